@@ -1,0 +1,148 @@
+/*
+ * lasso_b200.h -- C ABI of the B200-native ISTA/FISTA sparse-encode engine.
+ *
+ * The reference (rfeinman/pytorch-lasso) has no FFI: its "operator API" is the
+ * Python functions lasso.linear.sparse_encode / dict_learning / solvers.ista.
+ * Each entry point below replaces the arithmetic of one reference call site
+ * (file:line relative to the reference checkout) and is what a ctypes binding
+ * on the reference side would call.
+ *
+ * Conventions
+ *   - all matrices are row-major, contiguous, float32:
+ *       x[n,d]  weight[d,k] (atoms are COLUMNS)  z[n,k]
+ *   - "device" entry points take device pointers valid on the current CUDA
+ *     device and a cudaStream_t passed as void*; they never synchronise unless
+ *     stated.  "_host" entry points take host pointers, do the H2D / D2H copies
+ *     themselves and return after the result is in the host buffer.
+ *   - the caller owns every buffer passed in; the library owns only its private
+ *     workspace (freed by lasso_b200_release_workspace or at process exit).
+ *   - return value: 0 on success, negative lasso_b200_status on failure;
+ *     lasso_b200_last_error() gives a thread-local message.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns LASSO_B200_ERR_CUDA.
+ */
+#ifndef LASSO_B200_H_
+#define LASSO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum lasso_b200_status {
+  LASSO_B200_OK = 0,
+  LASSO_B200_ERR_INVALID = -1,     /* bad argument (shape, null pointer, flag)   */
+  LASSO_B200_ERR_CUDA = -2,        /* CUDA runtime / driver failure               */
+  LASSO_B200_ERR_UNSUPPORTED = -3, /* shape or option not supported by this path  */
+  LASSO_B200_ERR_NOMEM = -4        /* workspace allocation failed                 */
+} lasso_b200_status;
+
+/* which inner-loop kernel lasso_b200_fista_f32 uses */
+typedef enum lasso_b200_path {
+  LASSO_B200_PATH_AUTO = 0,   /* tcgen05 kernel when the shape fits, else FFMA      */
+  LASSO_B200_PATH_FFMA = 1,   /* CUDA-core fp32 FFMA kernel: any n, d, k            */
+  LASSO_B200_PATH_TCGEN05 = 2 /* tcgen05 / TMEM tensor-core kernel (split bf16x3)   */
+} lasso_b200_path;
+
+/* ABI version: major*1000 + minor */
+int32_t lasso_b200_version(void);
+
+/* message of the last failure on this thread ("" if none) */
+const char* lasso_b200_last_error(void);
+
+/* path that lasso_b200_fista_f32 would take for (n,d,k) with LASSO_B200_PATH_AUTO */
+int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k);
+
+/* number of kernels this library has launched in this process (bench: gpu_launches) */
+int64_t lasso_b200_launch_count(void);
+
+/*
+ * ISTA / FISTA solve -- replaces the loop of lasso/linear/solvers/ista.py:57-104
+ * (gradient step ista.py:71-73,90; stop test ista.py:64,93-95; momentum
+ * ista.py:77-78,98-101) for backtrack=False.
+ *
+ *   x, weight      device, read-only
+ *   z0             device [n,k] or NULL for the all-zero start (sparse_encode.py:23)
+ *   z_out          device [n,k]; receives the returned code.  May alias z0.
+ *   alpha, lr      python floats of the reference (double); the library rounds
+ *                  lr and alpha*lr to float32 exactly as torch does
+ *   maxiter        >= 0;  0 copies z0 (or zeros) to z_out
+ *   fast           non-zero = FISTA momentum
+ *   tol_abs        absolute threshold of the batch-global stop test, i.e. the
+ *                  reference's z0.numel()*tol.  Negative disables the test.
+ *   iters_done     optional HOST pointer: number of iterations executed (forces
+ *                  one stream synchronisation when non-NULL)
+ *   delta_hist     optional DEVICE pointer to maxiter doubles: sum|z_i - z_{i+1}|
+ *                  of every executed iteration (0 for skipped ones)
+ *   path           lasso_b200_path
+ */
+int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z0,
+                             float* z_out, int64_t n, int32_t d, int32_t k,
+                             double alpha, double lr, int32_t maxiter, int32_t fast,
+                             double tol_abs, int32_t* iters_done, double* delta_hist,
+                             int32_t path, void* stream);
+
+/*
+ * Same solve on HOST buffers (pinned or pageable): copies x, weight (and z0)
+ * to the current device, runs lasso_b200_fista_f32, copies the code back and
+ * synchronises.  delta_hist, if given, is a HOST pointer here.
+ */
+int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const float* z0,
+                                  float* z_out, int64_t n, int32_t d, int32_t k,
+                                  double alpha, double lr, int32_t maxiter, int32_t fast,
+                                  double tol_abs, int32_t* iters_done, double* delta_hist,
+                                  int32_t path);
+
+/*
+ * Lipschitz constant L = lambda_max(W^T W) -- replaces _lipschitz_constant,
+ * ista.py:8-14 (Gram + D2H + ARPACK eigsh) by an on-device float64 power
+ * iteration on the smaller Gram.  Synchronises; result in *l_out (host).
+ */
+int32_t lasso_b200_lipschitz_f32(const float* weight, int32_t d, int32_t k,
+                                 int32_t iters, double* l_out, void* stream);
+
+/*
+ * Loss terms of lasso_loss, dict_learning.py:10-13:
+ *   out[0] = sum (x - z weight^T)^2      out[1] = sum |z|
+ * out: DEVICE pointer to 2 doubles (overwritten).  The caller forms
+ * (0.5*out[0] + alpha*out[1]) / n  (after an all-reduce when sharded).
+ */
+int32_t lasso_b200_loss_terms_f32(const float* x, const float* z, const float* weight,
+                                  int64_t n, int32_t d, int32_t k, double* out,
+                                  void* stream);
+
+/*
+ * Sufficient statistics of the dictionary update (M-step):
+ *   gram_zz[k,k] = z^T z     gram_zx[k,d] = z^T x      (float64, overwritten)
+ * Replaces the data passes of update_dict (dict_learning.py:82-101) and
+ * update_dict_ridge (dict_learning.py:117-118); these are the buffers that are
+ * all-reduced across GPUs.
+ */
+int32_t lasso_b200_gram_f32(const float* z, const float* x, int64_t n, int32_t d,
+                            int32_t k, double* gram_zz, double* gram_zx, void* stream);
+
+/*
+ * Gauss-Seidel atom sweep of update_dict (dict_learning.py:83-101) in Gram
+ * space, one CTA:  u_j = B[j] - D A[:,j] + A[j,j] d_j ; d_j = u_j/|u_j|.
+ *   dict      device [d,k] float32, updated in place
+ *   gram_zz   device [k,k] float64 (rows/cols of re-drawn atoms are zeroed)
+ *   gram_zx   device [k,d] float64
+ *   redraw    device [d,k] float32 N(0,1) draws that replace degenerate atoms
+ *             (|u_j| < eps, dict_learning.py:91-98), or NULL: the atom is then
+ *             left for the caller to re-draw (its statistics are zeroed either way)
+ *   zeroed    device [k] int32: 1 for degenerate atoms -- the caller must zero
+ *             the code column z[:,j] (dict_learning.py:98)
+ */
+int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gram_zx,
+                                        int32_t d, int32_t k, double eps,
+                                        const float* redraw, int32_t* zeroed,
+                                        void* stream);
+
+/* free the per-device private workspace (buffers are re-grown on demand) */
+int32_t lasso_b200_release_workspace(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASSO_B200_H_ */

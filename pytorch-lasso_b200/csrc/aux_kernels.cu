@@ -1,0 +1,295 @@
+// Small kernels around the FISTA loop: Lipschitz constant (power iteration),
+// M-step sufficient statistics (Gram matrices) and the Gram-space atom sweep.
+#include "common.cuh"
+
+namespace lasso {
+namespace {
+
+// ---------------------------------------------------------------------------
+// K2: L = lambda_max(W^T W) = lambda_max(W W^T)        (ista.py:8-14)
+// ---------------------------------------------------------------------------
+// small symmetric Gram in float64: m = min(d,k); M = W W^T (d<=k) or W^T W.
+__global__ void small_gram_kernel(const float* __restrict__ w, int d, int k, int m, int len,
+                                  int row_gram, double* __restrict__ gram) {
+  __shared__ double ta[16][17], tb[16][17];
+  const int a = blockIdx.y * 16 + threadIdx.y;
+  const int b = blockIdx.x * 16 + threadIdx.x;
+  double acc = 0.0;
+  for (int c0 = 0; c0 < len; c0 += 16) {
+    // element (row r of the Gram, contraction index c)
+    const int ca = c0 + threadIdx.x;
+    const int ra = blockIdx.y * 16 + threadIdx.y;
+    const int rb = blockIdx.x * 16 + threadIdx.y;
+    double va = 0.0, vb = 0.0;
+    if (ca < len) {
+      if (ra < m) va = row_gram ? (double)w[(int64_t)ra * k + ca] : (double)w[(int64_t)ca * k + ra];
+      if (rb < m) vb = row_gram ? (double)w[(int64_t)rb * k + ca] : (double)w[(int64_t)ca * k + rb];
+    }
+    ta[threadIdx.y][threadIdx.x] = va;
+    tb[threadIdx.y][threadIdx.x] = vb;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc += ta[threadIdx.y][c] * tb[threadIdx.x][c];
+    __syncthreads();
+  }
+  if (a < m && b < m) gram[(int64_t)a * m + b] = acc;
+}
+
+// one CTA: normalised power iteration on the m x m Gram, Rayleigh quotient out.
+__global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restrict__ gram, int m,
+                                                          int iters, double* __restrict__ vec,
+                                                          double* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double s_norm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  double* v = vec;       // [m]
+  double* u = vec + m;   // [m]
+  for (int a = tid; a < m; a += blockDim.x) {
+    // deterministic, non-symmetric start vector
+    unsigned h = (unsigned)a * 2654435761u;
+    v[a] = 1.0 + 0.25 * (double)((h >> 8) & 0xffff) / 65536.0;
+  }
+  __syncthreads();
+  double lambda = 0.0, prev = -1.0;
+  int stable = 0;
+  for (int it = 0; it < iters; ++it) {
+    for (int a = warp; a < m; a += nwarps) {
+      double s = 0.0;
+      for (int c = lane; c < m; c += 32) s += gram[(int64_t)a * m + c] * v[c];
+      s = warp_sum(s);
+      if (lane == 0) u[a] = s;
+    }
+    __syncthreads();
+    double part = 0.0, dotp = 0.0;
+    for (int a = tid; a < m; a += blockDim.x) {
+      part += u[a] * u[a];
+      dotp += u[a] * v[a];
+    }
+    part = warp_sum(part);
+    dotp = warp_sum(dotp);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int wi = 0; wi < nwarps; ++wi) s += red[wi];
+      s_norm = s;
+    }
+    __syncthreads();
+    const double nn = s_norm;
+    if (lane == 0) red[warp] = dotp;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int wi = 0; wi < nwarps; ++wi) s += red[wi];
+      red[0] = s;
+    }
+    __syncthreads();
+    // v was unit-norm (after the first step), so v^T M v = <u, v> is the Rayleigh quotient
+    const double vv_dot = red[0];
+    const double nrm = sqrt(nn);
+    __syncthreads();
+    if (nrm == 0.0) {
+      lambda = 0.0;
+      break;
+    }
+    for (int a = tid; a < m; a += blockDim.x) v[a] = u[a] / nrm;
+    __syncthreads();
+    if (it > 0) {
+      lambda = vv_dot;
+      if (fabs(lambda - prev) <= 1e-15 * fabs(lambda)) {
+        if (++stable >= 3) break;
+      } else {
+        stable = 0;
+      }
+      prev = lambda;
+    }
+  }
+  if (tid == 0) out[0] = lambda;
+}
+
+// ---------------------------------------------------------------------------
+// K3: gram_zz = Z^T Z (k x k), gram_zx = Z^T X (k x d), float64 outputs
+// ---------------------------------------------------------------------------
+constexpr int kGT = 64;      // output tile
+constexpr int kGR = 32;      // rows staged per step
+constexpr int kGSlab = 512;  // rows per CTA
+
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ z,
+                                                   const float* __restrict__ x, int64_t n, int d,
+                                                   int k, double* __restrict__ gzz,
+                                                   double* __restrict__ gzx) {
+  __shared__ __align__(16) float As[kGR][kGT + 4];
+  __shared__ __align__(16) float Bs[kGR][kGT + 4];
+  const int nbj = (k + d + kGT - 1) / kGT;
+  const int bi = blockIdx.y / nbj, bj = blockIdx.y % nbj;
+  const int a0 = bi * kGT;   // atom block
+  const int c0 = bj * kGT;   // column block of [Z | X]
+  const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+  const int64_t r_begin = (int64_t)blockIdx.x * kGSlab;
+  const int64_t r_end = min(n, r_begin + kGSlab);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += kGR) {
+    __syncthreads();
+    for (int e = tid; e < kGR * kGT; e += 256) {
+      const int rr = e / kGT, cc = e % kGT;
+      const int64_t gr = r0 + rr;
+      float va = 0.f, vb = 0.f;
+      if (gr < r_end) {
+        if (a0 + cc < k) va = z[gr * k + a0 + cc];
+        const int c = c0 + cc;
+        if (c < k) vb = z[gr * k + c];
+        else if (c < k + d) vb = x[gr * d + (c - k)];
+      }
+      As[rr][cc] = va;
+      Bs[rr][cc] = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < kGR; ++rr) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[rr][ta * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[rr][tb * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = a0 + ta * 4 + i, c = c0 + tb * 4 + j;
+      if (a >= k || acc[i][j] == 0.f) continue;
+      if (c < k) atomicAdd(&gzz[(int64_t)a * k + c], (double)acc[i][j]);
+      else if (c < k + d) atomicAdd(&gzx[(int64_t)a * d + (c - k)], (double)acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: Gauss-Seidel atom sweep in Gram space, one CTA   (dict_learning.py:83-101)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) dict_sweep_kernel(float* dict, double* gzz, double* gzx,
+                                                          int d, int k, double eps,
+                                                          const float* __restrict__ redraw,
+                                                          int* __restrict__ zeroed,
+                                                          double* __restrict__ u) {
+  __shared__ double red[32];
+  __shared__ double s_val;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int j = 0; j < k; ++j) {
+    const double ajj = gzz[(int64_t)j * k + j];
+    // u_i = B[j,i] - sum_l D[i,l] A[l,j] + A[j,j] D[i,j]      (A symmetric: A[l,j] = A[j,l])
+    for (int i = warp; i < d; i += nwarps) {
+      double s = 0.0;
+      for (int l = lane; l < k; l += 32)
+        s += (double)dict[(int64_t)i * k + l] * gzz[(int64_t)j * k + l];
+      s = warp_sum(s);
+      if (lane == 0) u[i] = gzx[(int64_t)j * d + i] - s + ajj * (double)dict[(int64_t)i * k + j];
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int i = tid; i < d; i += blockDim.x) part += u[i] * u[i];
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int wi = 0; wi < nwarps; ++wi) s += red[wi];
+      s_val = sqrt(s);
+    }
+    __syncthreads();
+    double nrm = s_val;
+    const bool degenerate = nrm < eps;
+    if (degenerate) {
+      // the atom's codes are dropped (dict_learning.py:92-98): its row/column of the
+      // statistics vanish, so the replacement never influences the later atoms
+      for (int l = tid; l < k; l += blockDim.x) {
+        gzz[(int64_t)j * k + l] = 0.0;
+        gzz[(int64_t)l * k + j] = 0.0;
+      }
+      for (int i = tid; i < d; i += blockDim.x) gzx[(int64_t)j * d + i] = 0.0;
+      if (tid == 0) zeroed[j] = 1;
+      nrm = 0.0;
+      if (redraw != nullptr) {
+        __syncthreads();
+        part = 0.0;
+        for (int i = tid; i < d; i += blockDim.x) {
+          const double r = (double)redraw[(int64_t)i * k + j];
+          u[i] = r;
+          part += r * r;
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+          double s = 0.0;
+          for (int wi = 0; wi < nwarps; ++wi) s += red[wi];
+          s_val = sqrt(s);
+        }
+        __syncthreads();
+        nrm = s_val;
+      }
+    } else if (tid == 0) {
+      zeroed[j] = 0;
+    }
+    if (nrm > 0.0) {
+      for (int i = tid; i < d; i += blockDim.x) dict[(int64_t)i * k + j] = (float)(u[i] / nrm);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
+                  cudaStream_t st) {
+  // scratch: [m*m] Gram + [2*m] vectors
+  const int row_gram = d <= k ? 1 : 0;
+  const int m = row_gram ? d : k;
+  const int len = row_gram ? k : d;
+  dim3 grid((m + 15) / 16, (m + 15) / 16), block(16, 16);
+  small_gram_kernel<<<grid, block, 0, st>>>(w, d, k, m, len, row_gram, scratch);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  power_iter_kernel<<<1, 1024, 0, st>>>(scratch, m, iters, scratch + (size_t)m * m, l_dev);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  return LASSO_B200_OK;
+}
+
+int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz, double* gzx,
+             cudaStream_t st) {
+  LASSO_CUDA_TRY(cudaMemsetAsync(gzz, 0, sizeof(double) * (size_t)k * k, st));
+  LASSO_CUDA_TRY(cudaMemsetAsync(gzx, 0, sizeof(double) * (size_t)k * d, st));
+  if (n == 0) return LASSO_B200_OK;
+  const int nbi = (k + kGT - 1) / kGT, nbj = (k + d + kGT - 1) / kGT;
+  dim3 grid((unsigned)((n + kGSlab - 1) / kGSlab), (unsigned)(nbi * nbj));
+  gram_kernel<<<grid, 256, 0, st>>>(z, x, n, d, k, gzz, gzx);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  return LASSO_B200_OK;
+}
+
+int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
+                    const float* redraw, int* zeroed, cudaStream_t st) {
+  double* u = nullptr;
+  LASSO_CUDA_TRY(cudaMallocAsync(&u, sizeof(double) * (size_t)d, st));
+  dict_sweep_kernel<<<1, 1024, 0, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed, u);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(u, st);
+  if (e != cudaSuccess) {
+    set_error("dict_sweep_kernel launch failed: %s", cudaGetErrorString(e));
+    return LASSO_B200_ERR_CUDA;
+  }
+  count_launch();
+  return LASSO_B200_OK;
+}
+
+}  // namespace lasso

@@ -1,0 +1,367 @@
+// extern "C" entry points declared in include/lasso_b200.h: argument checks,
+// private workspace, buffer rotation of the FISTA loop, result selection.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace lasso {
+
+std::atomic<long long> g_launches{0};
+static thread_local char t_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// ---- grow-only device workspace, one per device ----------------------------
+struct Buffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+struct Workspace {
+  Buffer code;     // second code buffer [n,k]
+  Buffer hist;     // per-iteration delta sums (double)
+  Buffer ctl;      // small scalars (int/double)
+  Buffer scratch;  // Lipschitz Gram etc.
+  Buffer hx, hw, hz;  // device copies for the _host entry points
+};
+constexpr int kMaxDevices = 64;
+Workspace g_ws[kMaxDevices];
+std::mutex g_ws_mutex;
+
+int ensure(Buffer& b, size_t bytes) {
+  if (bytes <= b.bytes) return LASSO_B200_OK;
+  if (b.ptr) {
+    cudaError_t e = cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+    if (e != cudaSuccess) {
+      set_error("cudaFree failed: %s", cudaGetErrorString(e));
+      return LASSO_B200_ERR_CUDA;
+    }
+  }
+  cudaError_t e = cudaMalloc(&b.ptr, bytes);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? LASSO_B200_ERR_NOMEM : LASSO_B200_ERR_CUDA;
+  }
+  b.bytes = bytes;
+  return LASSO_B200_OK;
+}
+
+int current_workspace(Workspace** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("no usable CUDA device: %s", cudaGetErrorString(e));
+    return LASSO_B200_ERR_CUDA;
+  }
+  if (dev < 0 || dev >= kMaxDevices) {
+    set_error("device ordinal %d out of range", dev);
+    return LASSO_B200_ERR_INVALID;
+  }
+  *out = &g_ws[dev];
+  return LASSO_B200_OK;
+}
+
+// first iteration whose delta met the stop test, else maxiter-1; result index
+// written to ctl[0] = number of executed iterations.
+__global__ void find_stop_kernel(const double* __restrict__ hist, int maxiter, double tol_abs,
+                                 int lag_extra, int* __restrict__ ctl) {
+  // single thread: maxiter is small (tens to thousands)
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int done = maxiter;
+  if (tol_abs >= 0.0) {
+    for (int i = 0; i < maxiter - 1; ++i)
+      if (hist[i] <= tol_abs) {
+        done = i + 1;
+        break;
+      }
+  }
+  ctl[0] = done;
+  (void)lag_extra;
+}
+
+// copy the buffer that holds z_done into z_out when it is not already there
+__global__ void select_result_kernel(const float* __restrict__ z_a, const float* __restrict__ z_b,
+                                     float* __restrict__ z_out, int64_t count,
+                                     const int* __restrict__ ctl) {
+  const int done = ctl[0];
+  const float* src = (done & 1) ? z_b : z_a;  // z_i lives in (i even ? z_a : z_b)
+  if (src == z_out) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    z_out[i] = src[i];
+}
+
+int check_problem(const void* x, const void* w, const void* z_out, int64_t n, int d, int k) {
+  if (n < 0 || d <= 0 || k <= 0) {
+    set_error("invalid shape n=%lld d=%d k=%d", (long long)n, d, k);
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (n > 0 && (!x || !z_out)) {
+    set_error("null x / z_out pointer");
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (!w) {
+    set_error("null weight pointer");
+    return LASSO_B200_ERR_INVALID;
+  }
+  return LASSO_B200_OK;
+}
+
+}  // namespace
+}  // namespace lasso
+
+using namespace lasso;
+
+extern "C" {
+
+int32_t lasso_b200_version(void) { return 1000; }
+
+const char* lasso_b200_last_error(void) { return t_error; }
+
+int64_t lasso_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k) {
+  return fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
+}
+
+int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z0, float* z_out,
+                             int64_t n, int32_t d, int32_t k, double alpha, double lr,
+                             int32_t maxiter, int32_t fast, double tol_abs, int32_t* iters_done,
+                             double* delta_hist, int32_t path, void* stream) {
+  t_error[0] = 0;
+  int rc = check_problem(x, weight, z_out, n, d, k);
+  if (rc) return rc;
+  if (maxiter < 0 || !(lr > 0.0) || !std::isfinite(lr) || !std::isfinite(alpha)) {
+    set_error("invalid maxiter=%d / lr=%g / alpha=%g", maxiter, lr, alpha);
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (path == LASSO_B200_PATH_AUTO) path = lasso_b200_select_path(n, d, k);
+  if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05) {
+    set_error("unknown path %d", path);
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) {
+    set_error("tcgen05 path does not take n=%lld d=%d k=%d", (long long)n, d, k);
+    return LASSO_B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t code_bytes = sizeof(float) * (size_t)n * (size_t)k;
+
+  if (n == 0) {
+    if (iters_done) *iters_done = 0;
+    return LASSO_B200_OK;
+  }
+  if (maxiter == 0) {
+    if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_out, 0, code_bytes, st));
+    else if (z0 != z_out)
+      LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
+    if (iters_done) *iters_done = 0;
+    return LASSO_B200_OK;
+  }
+
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  Workspace* ws = nullptr;
+  rc = current_workspace(&ws);
+  if (rc) return rc;
+  if ((rc = ensure(ws->code, code_bytes))) return rc;
+  if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
+  if ((rc = ensure(ws->ctl, 256))) return rc;
+
+  // z_i lives in (i even ? z_a : z_b); put z_maxiter into z_out without a copy
+  float* wsbuf = (float*)ws->code.ptr;
+  float* z_a = (maxiter & 1) ? wsbuf : z_out;
+  float* z_b = (maxiter & 1) ? z_out : wsbuf;
+  if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_a, 0, code_bytes, st));
+  else if (z0 != z_a)
+    LASSO_CUDA_TRY(cudaMemcpyAsync(z_a, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
+  double* hist = (double*)ws->hist.ptr;
+  LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+
+  FistaArgs a{};
+  a.x = x;
+  a.w = weight;
+  a.z_a = z_a;
+  a.z_b = z_b;
+  a.n = n;
+  a.d = d;
+  a.k = k;
+  a.lr = (float)lr;               // torch rounds the python scalar to the tensor dtype
+  a.lam = (float)(alpha * lr);    // softshrink lambda = alpha*lr, product in double (ista.py:90)
+  a.maxiter = maxiter;
+  a.fast = fast ? 1 : 0;
+  a.tol_abs = tol_abs;
+  a.hist = hist;
+  rc = (path == LASSO_B200_PATH_TCGEN05) ? fista_tc_run(a, z_out, st) : fista_ffma_run(a, z_out, st);
+  if (rc) return rc;
+
+  int* ctl = (int*)ws->ctl.ptr;
+  if (tol_abs >= 0.0 || iters_done) {
+    find_stop_kernel<<<1, 32, 0, st>>>(hist, maxiter, tol_abs, 0, ctl);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+  }
+  if (tol_abs >= 0.0) {
+    int blocks = (int)std::min<int64_t>(((int64_t)n * k + 1023) / 1024, 148 * 8);
+    select_result_kernel<<<blocks, 256, 0, st>>>(z_a, z_b, z_out, (int64_t)n * k, ctl);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+  }
+  if (delta_hist)
+    LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, hist, sizeof(double) * (size_t)maxiter,
+                                   cudaMemcpyDeviceToDevice, st));
+  if (iters_done) {
+    int done = 0;
+    LASSO_CUDA_TRY(cudaMemcpyAsync(&done, ctl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+    *iters_done = done;
+  }
+  return LASSO_B200_OK;
+}
+
+int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const float* z0,
+                                  float* z_out, int64_t n, int32_t d, int32_t k, double alpha,
+                                  double lr, int32_t maxiter, int32_t fast, double tol_abs,
+                                  int32_t* iters_done, double* delta_hist, int32_t path) {
+  t_error[0] = 0;
+  int rc = check_problem(x, weight, z_out, n, d, k);
+  if (rc) return rc;
+  if (maxiter < 0) {
+    set_error("invalid maxiter=%d", maxiter);
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (n == 0) {
+    if (iters_done) *iters_done = 0;
+    return LASSO_B200_OK;
+  }
+  const size_t xb = sizeof(float) * (size_t)n * d, wb = sizeof(float) * (size_t)d * k;
+  const size_t zb = sizeof(float) * (size_t)n * k;
+  float *dx, *dw, *dz;
+  double* dh = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace* ws = nullptr;
+    if ((rc = current_workspace(&ws))) return rc;
+    if ((rc = ensure(ws->hx, xb))) return rc;
+    if ((rc = ensure(ws->hw, wb))) return rc;
+    if ((rc = ensure(ws->hz, zb + sizeof(double) * (size_t)(maxiter + 1)))) return rc;
+    dx = (float*)ws->hx.ptr;
+    dw = (float*)ws->hw.ptr;
+    dz = (float*)ws->hz.ptr;
+    if (delta_hist) dh = (double*)((char*)ws->hz.ptr + ((zb + 7) & ~(size_t)7));
+  }
+  cudaStream_t st = nullptr;  // legacy default stream: ordered with the copies below
+  LASSO_CUDA_TRY(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, st));
+  LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
+  if (z0) LASSO_CUDA_TRY(cudaMemcpyAsync(dz, z0, zb, cudaMemcpyHostToDevice, st));
+  rc = lasso_b200_fista_f32(dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, maxiter, fast,
+                            tol_abs, nullptr, dh, path, st);
+  if (rc) return rc;
+  LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, dz, zb, cudaMemcpyDeviceToHost, st));
+  if (delta_hist && maxiter > 0)
+    LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, dh, sizeof(double) * (size_t)maxiter,
+                                   cudaMemcpyDeviceToHost, st));
+  LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+  if (iters_done) {
+    // recompute on the host from the history when it was requested, else re-run the scan
+    int done = maxiter;
+    if (tol_abs >= 0.0 && maxiter > 0) {
+      std::lock_guard<std::mutex> lock(g_ws_mutex);
+      Workspace* ws = nullptr;
+      if ((rc = current_workspace(&ws))) return rc;
+      LASSO_CUDA_TRY(cudaMemcpy(&done, ws->ctl.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    *iters_done = done;
+  }
+  return LASSO_B200_OK;
+}
+
+int32_t lasso_b200_lipschitz_f32(const float* weight, int32_t d, int32_t k, int32_t iters,
+                                 double* l_out, void* stream) {
+  t_error[0] = 0;
+  if (!weight || !l_out || d <= 0 || k <= 0 || iters <= 0) {
+    set_error("invalid argument to lipschitz");
+    return LASSO_B200_ERR_INVALID;
+  }
+  const int m = d <= k ? d : k;
+  if (m > 4096) {
+    set_error("lipschitz: min(d,k)=%d exceeds 4096", m);
+    return LASSO_B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  Workspace* ws = nullptr;
+  int rc = current_workspace(&ws);
+  if (rc) return rc;
+  if ((rc = ensure(ws->scratch, sizeof(double) * ((size_t)m * m + 2 * (size_t)m + 8)))) return rc;
+  double* scratch = (double*)ws->scratch.ptr;
+  double* l_dev = scratch + (size_t)m * m + 2 * (size_t)m;
+  if ((rc = lipschitz_run(weight, d, k, iters, l_dev, scratch, st))) return rc;
+  LASSO_CUDA_TRY(cudaMemcpyAsync(l_out, l_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+  LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+  return LASSO_B200_OK;
+}
+
+int32_t lasso_b200_loss_terms_f32(const float* x, const float* z, const float* weight, int64_t n,
+                                  int32_t d, int32_t k, double* out, void* stream) {
+  t_error[0] = 0;
+  int rc = check_problem(x, weight, z, n, d, k);
+  if (rc) return rc;
+  if (!out) {
+    set_error("null out pointer");
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (n == 0) {
+    LASSO_CUDA_TRY(cudaMemsetAsync(out, 0, 2 * sizeof(double), (cudaStream_t)stream));
+    return LASSO_B200_OK;
+  }
+  return loss_terms_run(x, z, weight, n, d, k, out, (cudaStream_t)stream);
+}
+
+int32_t lasso_b200_gram_f32(const float* z, const float* x, int64_t n, int32_t d, int32_t k,
+                            double* gram_zz, double* gram_zx, void* stream) {
+  t_error[0] = 0;
+  if (n < 0 || d <= 0 || k <= 0 || !gram_zz || !gram_zx || (n > 0 && (!z || !x))) {
+    set_error("invalid argument to gram");
+    return LASSO_B200_ERR_INVALID;
+  }
+  return gram_run(z, x, n, d, k, gram_zz, gram_zx, (cudaStream_t)stream);
+}
+
+int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gram_zx, int32_t d,
+                                        int32_t k, double eps, const float* redraw,
+                                        int32_t* zeroed, void* stream) {
+  t_error[0] = 0;
+  if (!dict || !gram_zz || !gram_zx || !zeroed || d <= 0 || k <= 0) {
+    set_error("invalid argument to dict_update_gram");
+    return LASSO_B200_ERR_INVALID;
+  }
+  return dict_update_run(dict, gram_zz, gram_zx, d, k, eps, redraw, zeroed, (cudaStream_t)stream);
+}
+
+int32_t lasso_b200_release_workspace(void) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  Workspace* ws = nullptr;
+  int rc = current_workspace(&ws);
+  if (rc) return rc;
+  Buffer* all[] = {&ws->code, &ws->hist, &ws->ctl, &ws->scratch, &ws->hx, &ws->hw, &ws->hz};
+  for (Buffer* b : all) {
+    if (b->ptr) cudaFree(b->ptr);
+    b->ptr = nullptr;
+    b->bytes = 0;
+  }
+  return LASSO_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Shared host/device helpers of the lasso_b200 extension (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/lasso_b200.h"
+
+namespace lasso {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define LASSO_CUDA_TRY(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::lasso::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                         __FILE__, __LINE__);                                         \
+      return LASSO_B200_ERR_CUDA;                                                     \
+    }                                                                                 \
+  } while (0)
+
+#define LASSO_CHECK_LAUNCH()                                                          \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ::lasso::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \
+                         __FILE__, __LINE__);                                         \
+      return LASSO_B200_ERR_CUDA;                                                     \
+    }                                                                                 \
+  } while (0)
+
+// ---- per-iteration control block shared by all FISTA kernels ---------------
+// hist[i] = sum |z_i - z_{i+1}| of iteration i (double, device).  A kernel of
+// iteration i exits at once when an earlier iteration already met the stop
+// test, so the stream of launches needs no host synchronisation
+// (reference: one blocking sync per iteration at ista.py:93).
+struct StepCtl {
+  double* hist;     // [maxiter] device
+  double tol_abs;   // < 0 : stop test disabled
+  int iter;         // index of this iteration
+};
+
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ float soft_threshold(float v, float lam) {
+  // ATen softshrink: v > lam ? v - lam : (v < -lam ? v + lam : 0)   (ista.py:90)
+  return v > lam ? __fsub_rn(v, lam) : (v < -lam ? __fadd_rn(v, lam) : 0.0f);
+}
+
+__device__ __forceinline__ float momentum_point(float zc, float zp, float beta) {
+  // y = z_next + beta * (z_next - z), three roundings, no FMA (ista.py:100)
+  return __fadd_rn(zc, __fmul_rn(beta, __fsub_rn(zc, zp)));
+}
+
+__device__ __forceinline__ float ista_update(float y, float g, float lr, float lam) {
+  // softshrink(y - lr * g, alpha * lr), two roundings before the shrink (ista.py:90)
+  return soft_threshold(__fsub_rn(y, __fmul_rn(lr, g)), lam);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// true when an earlier iteration already satisfied the stop test
+__device__ __forceinline__ bool already_stopped(const StepCtl& c, int lookback) {
+  if (c.tol_abs < 0.0) return false;
+  for (int b = 1; b <= lookback; ++b) {
+    int j = c.iter - b;
+    if (j >= 0 && c.hist[j] <= c.tol_abs) return true;
+  }
+  return false;
+}
+
+// ---- launchers implemented in the .cu files ---------------------------------
+struct FistaArgs {
+  const float* x;
+  const float* w;
+  float* z_a;  // ping
+  float* z_b;  // pong
+  int64_t n;
+  int d, k;
+  float lr, lam;
+  int maxiter, fast;
+  double tol_abs;
+  double* hist;  // [maxiter] device, zero-initialised
+};
+
+int fista_ffma_run(const FistaArgs& a, float* z_out, cudaStream_t st);
+bool fista_tc_supported(int64_t n, int d, int k);
+int fista_tc_run(const FistaArgs& a, float* z_out, cudaStream_t st);
+
+int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
+                  cudaStream_t st);
+int loss_terms_run(const float* x, const float* z, const float* w, int64_t n, int d, int k,
+                   double* out, cudaStream_t st);
+int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz,
+             double* gzx, cudaStream_t st);
+int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
+                    const float* redraw, int* zeroed, cudaStream_t st);
+
+}  // namespace lasso

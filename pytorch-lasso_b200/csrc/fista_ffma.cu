@@ -1,0 +1,374 @@
+// CUDA-core (FFMA) FISTA step: one launch per iteration, any n, d, k.
+//
+// This is the exact-fp32 path of the engine and the fallback for shapes the
+// tcgen05 kernel does not take.  Per 64-row tile (TM = 64/32/16 by d):
+//
+//   phase 1  R = Y W^T - X          Y = z_cur + beta (z_cur - z_prev) recomputed
+//                                    from the two code buffers (ista.py:72, 100)
+//   phase 2  G = R W                 (ista.py:73)
+//   epilogue z_next = S(Y - lr G)    written over z_prev; sum|z_cur - z_next|
+//                                    goes to hist[iter]           (ista.py:90, 93)
+//
+// HBM traffic per iteration: n (d + 3k) floats (Y is never stored).  The
+// dictionary is re-read per tile from L2.  Both GEMM phases run a 4x4
+// register-blocked FFMA tile from padded shared memory.
+#include "common.cuh"
+
+namespace lasso {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBlk = 64;   // output block width (d-block in phase 1, atom chunk in phase 2)
+constexpr int kCk = 32;    // contraction chunk staged in shared memory
+constexpr int kPad = 4;    // row padding (floats) -> conflict-free 128-bit LDS
+
+__device__ __forceinline__ float4 ld4(const float* base, int64_t row, int col, int64_t nrows,
+                                      int ncols, int ld, bool vec_ok) {
+  // guarded, zero-padded load of base[row, col..col+3]
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= nrows || col >= ncols) return v;
+  const float* p = base + row * (int64_t)ld + col;
+  if (vec_ok && col + 3 < ncols) return *reinterpret_cast<const float4*>(p);
+  v.x = p[0];
+  if (col + 1 < ncols) v.y = p[1];
+  if (col + 2 < ncols) v.z = p[2];
+  if (col + 3 < ncols) v.w = p[3];
+  return v;
+}
+
+__device__ __forceinline__ void st4(float* base, int64_t row, int col, int64_t nrows, int ncols,
+                                    int ld, bool vec_ok, float4 v) {
+  if (row >= nrows || col >= ncols) return;
+  float* p = base + row * (int64_t)ld + col;
+  if (vec_ok && col + 3 < ncols) {
+    *reinterpret_cast<float4*>(p) = v;
+    return;
+  }
+  p[0] = v.x;
+  if (col + 1 < ncols) p[1] = v.y;
+  if (col + 2 < ncols) p[2] = v.z;
+  if (col + 3 < ncols) p[3] = v.w;
+}
+
+struct StepParams {
+  const float* x;
+  const float* w;
+  const float* z_cur;
+  float* z_io;  // holds z_prev on entry, z_next on exit
+  int64_t n;
+  int d, k;
+  float lr, lam, beta;
+  int use_prev;  // 0: Y = z_cur (first iteration or plain ISTA)
+  int mode;      // 0: FISTA step, 1: loss terms (sum r^2, sum |z|) into out2
+  double* out2;
+  StepCtl ctl;
+};
+
+// MODE 0 = iteration step, MODE 1 = loss terms only.
+template <int TM, int MODE>
+__global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
+  constexpr int RPT = TM / 16;  // rows per thread
+  extern __shared__ __align__(16) float smem[];
+  const int d_pad = (p.d + 3) & ~3;
+  const int r_ld = d_pad + kPad;
+  float* Rs = smem;                                   // [TM][r_ld]
+  float* As = Rs + TM * r_ld;                         // [TM][kCk + kPad]   (Y chunk)
+  float* Ws = As + TM * (kCk + kPad);                 // max([kBlk][kCk+kPad], [kCk][kBlk+kPad])
+  __shared__ double red[kThreads / 32][2];
+
+  if (MODE == 0 && p.ctl.tol_abs >= 0.0 && p.ctl.iter >= 1 &&
+      p.ctl.hist[p.ctl.iter - 1] <= p.ctl.tol_abs)
+    return;  // an earlier iteration met the stop test (ista.py:93-95)
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool kvec = (p.k & 3) == 0;
+  const bool dvec = (p.d & 3) == 0;
+  const int64_t ntiles = (p.n + TM - 1) / TM;
+  double acc_a = 0.0, acc_b = 0.0;  // MODE 0: delta ; MODE 1: sum r^2, sum |z|
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+
+    // ---------------- phase 1: R = Y W^T - X ------------------------------
+    for (int db = 0; db < p.d; db += kBlk) {
+      float acc[RPT][4];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+      for (int j0 = 0; j0 < p.k; j0 += kCk) {
+        __syncthreads();
+        // stage Y chunk [TM][kCk] and W chunk [kBlk][kCk]  (both contraction-contiguous)
+        for (int e = tid; e < TM * (kCk / 4); e += kThreads) {
+          const int r = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
+          float4 zc = ld4(p.z_cur, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+          if (MODE == 0 && p.use_prev) {
+            float4 zp = ld4(p.z_io, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+            zc.x = momentum_point(zc.x, zp.x, p.beta);
+            zc.y = momentum_point(zc.y, zp.y, p.beta);
+            zc.z = momentum_point(zc.z, zp.z, p.beta);
+            zc.w = momentum_point(zc.w, zp.w, p.beta);
+          }
+          if (MODE == 1 && db == 0)
+            acc_b += (double)(fabsf(zc.x) + fabsf(zc.y)) + (double)(fabsf(zc.z) + fabsf(zc.w));
+          *reinterpret_cast<float4*>(&As[r * (kCk + kPad) + c4]) = zc;
+        }
+        for (int e = tid; e < kBlk * (kCk / 4); e += kThreads) {
+          const int i = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
+          float4 wv = ld4(p.w, db + i, j0 + c4, p.d, p.k, p.k, kvec);
+          *reinterpret_cast<float4*>(&Ws[i * (kCk + kPad) + c4]) = wv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < kCk; jj += 4) {
+          float4 a[RPT], b[4];
+#pragma unroll
+          for (int r = 0; r < RPT; ++r)
+            a[r] = *reinterpret_cast<const float4*>(&As[(ty * RPT + r) * (kCk + kPad) + jj]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            b[c] = *reinterpret_cast<const float4*>(&Ws[(tx + 16 * c) * (kCk + kPad) + jj]);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[r][c] = fmaf(a[r].x, b[c].x, acc[r][c]);
+              acc[r][c] = fmaf(a[r].y, b[c].y, acc[r][c]);
+              acc[r][c] = fmaf(a[r].z, b[c].z, acc[r][c]);
+              acc[r][c] = fmaf(a[r].w, b[c].w, acc[r][c]);
+            }
+        }
+      }
+      // residual block -> shared (zero outside the problem)
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int lr_ = ty * RPT + r, i = db + tx + 16 * c;
+          const int64_t gr = row0 + lr_;
+          float v = 0.f;
+          if (gr < p.n && i < p.d) v = __fsub_rn(acc[r][c], p.x[gr * p.d + i]);
+          if (i < d_pad) Rs[lr_ * r_ld + i] = v;
+          if (MODE == 1) acc_a += (double)v * (double)v;
+        }
+    }
+    if (MODE == 1) continue;
+
+    // ---------------- phase 2: G = R W, fused update ----------------------
+    for (int j0 = 0; j0 < p.k; j0 += kBlk) {
+      float acc[RPT][4];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+      for (int i0 = 0; i0 < d_pad; i0 += kCk) {
+        __syncthreads();
+        // stage W chunk [kCk][kBlk] (output-contiguous)
+        for (int e = tid; e < kCk * (kBlk / 4); e += kThreads) {
+          const int ii = e / (kBlk / 4), c4 = (e % (kBlk / 4)) * 4;
+          float4 wv = ld4(p.w, i0 + ii, j0 + c4, p.d, p.k, p.k, kvec);
+          *reinterpret_cast<float4*>(&Ws[ii * (kBlk + kPad) + c4]) = wv;
+        }
+        __syncthreads();
+        const int imax = min(kCk, d_pad - i0);
+        for (int ii = 0; ii < imax; ii += 4) {
+          float4 a[RPT], b[4];
+#pragma unroll
+          for (int r = 0; r < RPT; ++r)
+            a[r] = *reinterpret_cast<const float4*>(&Rs[(ty * RPT + r) * r_ld + i0 + ii]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            b[q] = *reinterpret_cast<const float4*>(&Ws[(ii + q) * (kBlk + kPad) + tx * 4]);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            acc[r][0] = fmaf(a[r].x, b[0].x, acc[r][0]);
+            acc[r][1] = fmaf(a[r].x, b[0].y, acc[r][1]);
+            acc[r][2] = fmaf(a[r].x, b[0].z, acc[r][2]);
+            acc[r][3] = fmaf(a[r].x, b[0].w, acc[r][3]);
+            acc[r][0] = fmaf(a[r].y, b[1].x, acc[r][0]);
+            acc[r][1] = fmaf(a[r].y, b[1].y, acc[r][1]);
+            acc[r][2] = fmaf(a[r].y, b[1].z, acc[r][2]);
+            acc[r][3] = fmaf(a[r].y, b[1].w, acc[r][3]);
+            acc[r][0] = fmaf(a[r].z, b[2].x, acc[r][0]);
+            acc[r][1] = fmaf(a[r].z, b[2].y, acc[r][1]);
+            acc[r][2] = fmaf(a[r].z, b[2].z, acc[r][2]);
+            acc[r][3] = fmaf(a[r].z, b[2].w, acc[r][3]);
+            acc[r][0] = fmaf(a[r].w, b[3].x, acc[r][0]);
+            acc[r][1] = fmaf(a[r].w, b[3].y, acc[r][1]);
+            acc[r][2] = fmaf(a[r].w, b[3].z, acc[r][2]);
+            acc[r][3] = fmaf(a[r].w, b[3].w, acc[r][3]);
+          }
+        }
+      }
+      // epilogue: y recomputed from the code buffers, shrink, store over z_prev
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int64_t gr = row0 + ty * RPT + r;
+        const int col = j0 + tx * 4;
+        if (gr >= p.n || col >= p.k) continue;
+        float4 zc = ld4(p.z_cur, gr, col, p.n, p.k, p.k, kvec);
+        float4 y = zc;
+        if (p.use_prev) {
+          float4 zp = ld4(p.z_io, gr, col, p.n, p.k, p.k, kvec);
+          y.x = momentum_point(zc.x, zp.x, p.beta);
+          y.y = momentum_point(zc.y, zp.y, p.beta);
+          y.z = momentum_point(zc.z, zp.z, p.beta);
+          y.w = momentum_point(zc.w, zp.w, p.beta);
+        }
+        float4 zn;
+        zn.x = ista_update(y.x, acc[r][0], p.lr, p.lam);
+        zn.y = ista_update(y.y, acc[r][1], p.lr, p.lam);
+        zn.z = ista_update(y.z, acc[r][2], p.lr, p.lam);
+        zn.w = ista_update(y.w, acc[r][3], p.lr, p.lam);
+        st4(p.z_io, gr, col, p.n, p.k, p.k, kvec, zn);
+        float dsum = fabsf(__fsub_rn(zc.x, zn.x));
+        if (col + 1 < p.k) dsum += fabsf(__fsub_rn(zc.y, zn.y));
+        if (col + 2 < p.k) dsum += fabsf(__fsub_rn(zc.z, zn.z));
+        if (col + 3 < p.k) dsum += fabsf(__fsub_rn(zc.w, zn.w));
+        acc_a += (double)dsum;
+      }
+    }
+    (void)dvec;
+  }
+
+  // block reduction -> one double atomic per CTA
+  acc_a = warp_sum(acc_a);
+  acc_b = warp_sum(acc_b);
+  if ((tid & 31) == 0) {
+    red[tid >> 5][0] = acc_a;
+    red[tid >> 5][1] = acc_b;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double sa = 0.0, sb = 0.0;
+    for (int wi = 0; wi < kThreads / 32; ++wi) {
+      sa += red[wi][0];
+      sb += red[wi][1];
+    }
+    if (MODE == 0) {
+      if (p.ctl.hist) atomicAdd(&p.ctl.hist[p.ctl.iter], sa);
+    } else {
+      atomicAdd(&p.out2[0], sa);
+      atomicAdd(&p.out2[1], sb);
+    }
+  }
+}
+
+size_t smem_bytes(int tm, int d) {
+  const int d_pad = (d + 3) & ~3;
+  size_t ws = (size_t)max(kBlk * (kCk + kPad), kCk * (kBlk + kPad));
+  return sizeof(float) * ((size_t)tm * (d_pad + kPad) + (size_t)tm * (kCk + kPad) + ws);
+}
+
+int pick_tm(int d) {
+  const size_t budget = 200 * 1024;
+  if (smem_bytes(64, d) <= 96 * 1024) return 64;
+  if (smem_bytes(32, d) <= budget) return 32;
+  if (smem_bytes(16, d) <= budget) return 16;
+  return 0;
+}
+
+template <int TM, int MODE>
+int launch(const StepParams& p, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    LASSO_CUDA_TRY(cudaGetDevice(&dev));
+    LASSO_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const size_t smem = smem_bytes(TM, p.d);
+  static size_t configured = 0;
+  if (smem > configured) {
+    LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_ffma_kernel<TM, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int per_sm = 1;
+  LASSO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, fista_ffma_kernel<TM, MODE>, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t ntiles = (p.n + TM - 1) / TM;
+  int64_t grid = (int64_t)num_sms * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  fista_ffma_kernel<TM, MODE><<<(unsigned)grid, kThreads, smem, st>>>(p);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  return LASSO_B200_OK;
+}
+
+template <int MODE>
+int dispatch(const StepParams& p, cudaStream_t st) {
+  switch (pick_tm(p.d)) {
+    case 64: return launch<64, MODE>(p, st);
+    case 32: return launch<32, MODE>(p, st);
+    case 16: return launch<16, MODE>(p, st);
+    default:
+      set_error("FFMA path: d=%d needs more shared memory than one SM has", p.d);
+      return LASSO_B200_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+// Runs all iterations.  z_0 is in a.z_a; iteration i reads (i even ? z_a : z_b)
+// and writes the other buffer.  z_out is unused here (cabi.cu selects the
+// result buffer); kept in the signature for symmetry with the tcgen05 runner.
+int fista_ffma_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
+  double t = 1.0;
+  for (int it = 0; it < a.maxiter; ++it) {
+    StepParams p{};
+    p.x = a.x;
+    p.w = a.w;
+    p.z_cur = (it & 1) ? a.z_b : a.z_a;
+    p.z_io = (it & 1) ? a.z_a : a.z_b;
+    p.n = a.n;
+    p.d = a.d;
+    p.k = a.k;
+    p.lr = a.lr;
+    p.lam = a.lam;
+    // momentum coefficient that produced y_it, i.e. the one computed at the end
+    // of iteration it-1 (ista.py:99-100); doubles on the host like the reference
+    double beta = 0.0;
+    if (a.fast && it > 0) {
+      // t currently holds t_{it-1}; advance
+      const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
+      beta = (t - 1.0) / t_next;
+      t = t_next;
+    }
+    p.beta = (float)beta;
+    p.use_prev = (a.fast && it > 0) ? 1 : 0;
+    p.mode = 0;
+    p.out2 = nullptr;
+    p.ctl.hist = a.hist;
+    p.ctl.tol_abs = a.tol_abs;
+    p.ctl.iter = it;
+    int rc = dispatch<0>(p, st);
+    if (rc != LASSO_B200_OK) return rc;
+  }
+  return LASSO_B200_OK;
+}
+
+int loss_terms_run(const float* x, const float* z, const float* w, int64_t n, int d, int k,
+                   double* out, cudaStream_t st) {
+  LASSO_CUDA_TRY(cudaMemsetAsync(out, 0, 2 * sizeof(double), st));
+  StepParams p{};
+  p.x = x;
+  p.w = w;
+  p.z_cur = z;
+  p.z_io = nullptr;
+  p.n = n;
+  p.d = d;
+  p.k = k;
+  p.mode = 1;
+  p.out2 = out;
+  p.ctl.hist = nullptr;
+  p.ctl.tol_abs = -1.0;
+  p.ctl.iter = 0;
+  return dispatch<1>(p, st);
+}
+
+}  // namespace lasso

@@ -1,0 +1,131 @@
+"""ISTA / FISTA solver front end -- mirrors ``lasso.linear.solvers.ista``.
+
+Same signature, defaults and error behaviour as the reference function
+(lasso/linear/solvers/ista.py:57-58), but the loop of ista.py:79-102 runs in
+``liblasso_b200.so`` (one fused kernel per iteration, no host synchronisation
+between iterations).  Differences, all deliberate:
+
+* ``lr='auto'`` uses an on-device float64 power iteration instead of ARPACK on
+  the host (ista.py:8-14); the reference value itself varies ~1e-6 run to run.
+* the batch-global stop test (ista.py:93) is evaluated on the device; kernels
+  of later iterations turn into no-ops once it fires.
+* CPU tensors go through the C ABI's host entry point (H2D, solve, D2H) -- the
+  arithmetic always runs on the GPU.  There is no PyTorch fallback.
+* extra keyword ``path`` ('auto' | 'ffma' | 'tcgen05') selects the kernel, and
+  ``group`` a torch.distributed process group whose ranks hold row shards of one
+  batch (the stop test is then made global with one deferred all-reduce).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import utils as _utils
+from ... import _cabi
+
+__all__ = ["ista", "lipschitz_constant"]
+
+
+def lipschitz_constant(weight: torch.Tensor, iters: int = 2000) -> float:
+    """L = lambda_max(W^T W); replaces ``_lipschitz_constant`` (ista.py:8-14)."""
+    if weight.is_cuda:
+        return _cabi.lipschitz(weight.detach(), iters)
+    dev = _utils.default_device()
+    return _cabi.lipschitz(weight.detach().to(dev), iters)
+
+
+def _validate(x, z0, weight):
+    for name, t in (("x", x), ("weight", weight)) + ((("z0", z0),) if z0 is not None else ()):
+        if not torch.is_tensor(t):
+            raise TypeError("{} must be a tensor".format(name))
+        if t.dtype != torch.float32:
+            raise NotImplementedError(
+                "lasso_b200 computes in float32 only; {} has dtype {}".format(name, t.dtype))
+        if t.requires_grad:
+            raise NotImplementedError(
+                "lasso_b200 does not record an autograd graph through the solver; "
+                "detach {} first".format(name))
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[0]:
+        raise ValueError("expected x[n,d] and weight[d,k]; got {} and {}".format(
+            tuple(x.shape), tuple(weight.shape)))
+    if z0 is not None and tuple(z0.shape) != (x.shape[0], weight.shape[1]):
+        raise ValueError("z0 must have shape [n,k]")
+    if z0 is not None and z0.device != x.device:
+        raise ValueError("z0 and x must live on the same device")
+    if weight.device != x.device:
+        raise ValueError("weight and x must live on the same device")
+
+
+def _abs_tolerance(numel: int, tol: float) -> float:
+    # ista.py:64 -- python float; torch then compares the float32 sum against the
+    # scalar rounded to float32
+    return float(np.float32(numel * tol))
+
+
+def _first_stop(hist: torch.Tensor, tol_abs: float) -> int:
+    """Number of iterations the reference would have executed given the global deltas."""
+    hits = (hist[:-1] <= tol_abs).nonzero()
+    return int(hits[0]) + 1 if hits.numel() else int(hist.numel())
+
+
+def solve(x, z0, weight, alpha=1.0, fast=True, lr='auto', maxiter=10, tol=1e-5,
+          path='auto', group=None, return_iters=False, out=None):
+    """Shared implementation: ``z0`` may be None for the all-zero start; ``out`` is an
+    optional preallocated [n,k] float32 result buffer on x's device."""
+    _validate(x, z0, weight)
+    n, k = x.shape[0], weight.shape[1]
+    if lr == 'auto':
+        lr = 1.0 / lipschitz_constant(weight)
+    lr = float(lr)
+    alpha = float(alpha)
+    sharded = group is not None and torch.distributed.get_world_size(group) > 1
+    numel = n * k
+    if sharded:
+        cnt = torch.tensor([numel], dtype=torch.int64, device=x.device)
+        torch.distributed.all_reduce(cnt, group=group)
+        numel = int(cnt.item())
+    tol_abs = _abs_tolerance(numel, tol)
+
+    if not x.is_cuda:
+        if sharded:
+            raise NotImplementedError("sharded solves need CUDA tensors")
+        z, iters = _cabi.fista_host(x, weight, z0, alpha, lr, maxiter, fast, tol_abs,
+                                    path=path, want_iters=return_iters, out=out)
+        return (z, iters) if return_iters else z
+
+    if not sharded or maxiter <= 1:
+        z, iters, _ = _cabi.fista_device(x, weight, z0, alpha, lr, maxiter, fast, tol_abs,
+                                         path=path, want_iters=return_iters, out=out)
+        return (z, iters) if return_iters else z
+
+    # Row-sharded batch: run all iterations with the local test disabled, make the
+    # per-iteration deltas global with ONE all-reduce, and replay a shorter run in
+    # the (rare) case the global test fired early.  Deterministic kernels make the
+    # replay identical to stopping in place (ista.py:93-95 semantics).
+    z, _, hist = _cabi.fista_device(x, weight, z0, alpha, lr, maxiter, fast, -1.0,
+                                    path=path, want_hist=True, out=out)
+    torch.distributed.all_reduce(hist, group=group)
+    done = _first_stop(hist, tol_abs)
+    if done < maxiter:
+        z, _, _ = _cabi.fista_device(x, weight, z0, alpha, lr, done, fast, -1.0, path=path,
+                                     out=out)
+    return (z, done) if return_iters else z
+
+
+def ista(x, z0, weight, alpha=1.0, fast=True, lr='auto', maxiter=10,
+         tol=1e-5, backtrack=False, eta_backtrack=1.5, verbose=False,
+         path='auto', group=None, out=None):
+    """Drop-in for ``lasso.linear.solvers.ista`` (ista.py:57-104)."""
+    if backtrack:
+        if eta_backtrack <= 1:
+            raise ValueError('eta must be > 1.')  # ista.py:18-19
+        raise NotImplementedError(
+            "backtrack=True (ista.py:17-54) is not implemented in lasso_b200 yet")
+    if verbose:
+        raise NotImplementedError(
+            "verbose=True (per-iteration loss print, ista.py:80-81) is not implemented; "
+            "use linear.lasso_loss on the result")
+    if maxiter == 0:
+        return z0  # the reference returns the z0 object itself
+    return solve(x, z0, weight, alpha=alpha, fast=fast, lr=lr, maxiter=maxiter, tol=tol,
+                 path=path, group=group, out=out)

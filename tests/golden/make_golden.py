@@ -1,0 +1,149 @@
+"""Generate the golden fixtures in this directory from the REAL reference.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference package cannot be imported as shipped on scipy >= 1.12
+(lasso/linear/solvers/iterative_ridge.py:5 imports a private name that moved);
+the shim below restores that one name and nothing else.  Every case pins ``lr``
+to a float because the reference's lr='auto' (ARPACK on a float32 Gram) is not
+reproducible run to run.
+
+Fixtures are small compressed .npz files: inputs, the options used and the
+reference's outputs.  tests/test_oracle_golden.py checks the oracle against
+them on CPU; tests/test_gpu_parity.py checks the CUDA path against them.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+REFERENCE = "/root/reference"
+
+
+def import_reference():
+    import scipy.optimize.optimize as legacy  # noqa: F401  (deprecated alias module)
+    from scipy.optimize._optimize import _status_message
+    legacy._status_message = _status_message
+    sys.path.insert(0, REFERENCE)
+    import lasso.linear as ref_linear
+    from lasso.linear.solvers.ista import ista as ref_ista
+    return ref_linear, ref_ista
+
+
+def lipschitz64(w):
+    w64 = w.double()
+    return float(torch.linalg.eigvalsh(w64 @ w64.T)[-1])
+
+
+def main():
+    warnings.simplefilter("ignore")
+    import lasso_b200  # only for the seeded problem generator
+    from lasso_b200.testing import make_problem
+
+    torch.set_num_threads(1)  # the pinned-lr reference is thread-count independent; be safe
+    ref, ref_ista = import_reference()
+    out = {}
+
+    def save(name, **arrays):
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v))
+                                     for k, v in arrays.items()})
+        out[name] = os.path.getsize(path)
+
+    # ---- ISTA / FISTA solver cases -------------------------------------------------
+    cases = [
+        # name, n, d, k, kind, alpha, opts
+        ("ista_readme_fista", 128, 10, 50, "randn", 0.5, dict(fast=True, maxiter=10, tol=1e-5)),
+        ("ista_readme_plain", 128, 10, 50, "randn", 0.5, dict(fast=False, maxiter=25, tol=1e-5)),
+        ("ista_planted_200", 192, 64, 256, "planted", 0.1, dict(fast=True, maxiter=200, tol=0.0)),
+        ("ista_randn_200", 160, 64, 256, "randn", 0.1, dict(fast=True, maxiter=200, tol=0.0)),
+        ("ista_ragged", 77, 13, 37, "planted", 0.05, dict(fast=True, maxiter=60, tol=0.0)),
+        ("ista_wide_d", 50, 150, 90, "randn", 0.3, dict(fast=True, maxiter=40, tol=0.0)),
+        ("ista_earlystop", 64, 16, 32, "planted", 0.1, dict(fast=True, maxiter=500, tol=1e-3)),
+        ("ista_earlystop_plain", 64, 16, 32, "planted", 0.1, dict(fast=False, maxiter=500, tol=1e-3)),
+        ("ista_one_iter", 40, 8, 24, "randn", 0.2, dict(fast=True, maxiter=1, tol=1e-5)),
+        ("ista_big_alpha", 32, 8, 16, "randn", 50.0, dict(fast=True, maxiter=5, tol=0.0)),
+    ]
+    for name, n, d, k, kind, alpha, opts in cases:
+        x, w = make_problem(n, d, k, seed=len(name), kind=kind)
+        lr = 1.0 / lipschitz64(w)
+        z0 = torch.zeros(n, k)
+        z = ref_ista(x, z0, w, alpha=alpha, lr=lr, **opts)
+        save(name, x=x, weight=w, z0=z0, z=z, alpha=alpha, lr=lr,
+             fast=int(opts["fast"]), maxiter=opts["maxiter"], tol=opts["tol"])
+
+    # warm start from a non-zero code
+    x, w = make_problem(96, 20, 60, seed=7, kind="planted")
+    g = torch.Generator().manual_seed(11)
+    z0 = (torch.rand(96, 60, generator=g) - 0.5) * 0.2
+    lr = 1.0 / lipschitz64(w)
+    z = ref_ista(x, z0, w, alpha=0.1, lr=lr, fast=True, maxiter=15, tol=0.0)
+    save("ista_warmstart", x=x, weight=w, z0=z0, z=z, alpha=0.1, lr=lr, fast=1, maxiter=15, tol=0.0)
+
+    # backtracking line search (ista.py:17-54)
+    x, w = make_problem(48, 12, 30, seed=3, kind="randn")
+    lr = 4.0 / lipschitz64(w)  # deliberately too large so that the search shrinks it
+    z0 = torch.zeros(48, 30)
+    z = ref_ista(x, z0, w, alpha=0.2, lr=lr, fast=True, maxiter=20, tol=0.0, backtrack=True)
+    save("ista_backtrack", x=x, weight=w, z0=z0, z=z, alpha=0.2, lr=lr, fast=1, maxiter=20,
+         tol=0.0, backtrack=1, eta_backtrack=1.5)
+
+    # ---- sparse_encode boundary ------------------------------------------------------
+    x, w = make_problem(64, 10, 50, seed=5, kind="randn")
+    lr = 1.0 / lipschitz64(w)
+    for init in ("zero", "ridge", "transpose"):
+        z = ref.sparse_encode(x, w, alpha=0.5, algorithm="ista", init=init, lr=lr, maxiter=12,
+                              tol=0.0)
+        z0 = ref.initialize_code(x, w, 0.5, init)
+        save("encode_init_" + init, x=x, weight=w, z0=z0, z=z, alpha=0.5, lr=lr, fast=1,
+             maxiter=12, tol=0.0)
+
+    # ---- dictionary learning ---------------------------------------------------------
+    x, w = make_problem(128, 10, 50, seed=9, kind="planted")
+    z = ref.sparse_encode(x, w, alpha=0.2, algorithm="ista", lr=1.0 / lipschitz64(w), maxiter=30,
+                          tol=0.0)
+    ref_dl = sys.modules["lasso.linear.dict_learning"]  # the attribute is shadowed by the function
+    loss = ref_dl.lasso_loss(x, z, w, 0.2)
+    w_upd = ref_dl.update_dict(w.clone(), x, z.clone())
+    w_ridge = ref_dl.update_dict_ridge(x, z, lambd=1e-2)
+    save("mstep", x=x, weight=w, z=z, alpha=0.2, loss=loss, weight_update=w_upd,
+         weight_ridge=w_ridge, lambd=1e-2)
+
+    # degenerate atom: a code column that is all zero makes |u_j| < eps (dict_learning.py:91-98)
+    z_deg = z.clone()
+    z_deg[:, 3] = 0
+    z_deg[:, 17] = 0
+    torch.manual_seed(1234)
+    w_deg = ref_dl.update_dict(w.clone(), x, z_deg)
+    save("mstep_degenerate", x=x, weight=w, z=z_deg, weight_update=w_deg, zero_atoms=[3, 17])
+
+    for constrained in (True, False):
+        x, _ = make_problem(128, 10, 50, seed=21, kind="randn")
+        torch.manual_seed(0)
+        w0 = torch.empty(10, 50)
+        torch.nn.init.orthogonal_(w0)
+        if constrained:
+            w0 = torch.nn.functional.normalize(w0, dim=0)
+        torch.manual_seed(0)
+        # lr='auto' is what dict_learning users get; its ARPACK value wobbles ~1e-6, which
+        # the comparison tolerance of the dict_learning tests accounts for
+        w_fin, losses = ref.dict_learning(x, 50, alpha=0.5, constrained=constrained, steps=8,
+                                          lambd=1e-2, progbar=False, algorithm="ista", maxiter=10)
+        save("dict_learning_" + ("constrained" if constrained else "ridge"), x=x, weight0=w0,
+             weight=w_fin, losses=losses, alpha=0.5, steps=8, lambd=1e-2, maxiter=10)
+
+    for name, size in sorted(out.items()):
+        print("{:32s} {:8d} bytes".format(name, size))
+
+
+if __name__ == "__main__":
+    main()

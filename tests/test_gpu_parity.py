@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden vectors and the
+CPU oracle.  Tolerance: 1e-5 relative Frobenius on the returned coefficients
+(BASELINE.json north_star); the float32 reference itself sits 5e-7..3e-6 from float64."""
+import numpy as np
+import pytest
+import torch
+
+import lasso_b200
+import oracle
+from conftest import SOLVER_CASES, load_golden
+from lasso_b200 import _cabi
+from lasso_b200.linear import (dict_evaluate, dict_learning, lasso_loss, sparse_encode,
+                               update_dict, update_dict_ridge)
+from lasso_b200.linear.solvers import ista, lipschitz_constant
+from lasso_b200.testing import make_problem, rel_fro, support_mismatch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+PATHS = ["ffma", "auto"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    lasso_b200._cabi.load()  # fail loudly if the extension is missing
+    return torch.device("cuda", 0)
+
+
+def run_case(g, dev, path, **extra):
+    z0 = g["z0"].to(dev)
+    return ista(g["x"].to(dev), z0, g["weight"].to(dev), alpha=g["alpha"], fast=bool(g["fast"]),
+                lr=g["lr"], maxiter=int(g["maxiter"]), tol=g["tol"], path=path, **extra)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", SOLVER_CASES)
+def test_golden_solver_cases(dev, name, path):
+    g = load_golden(name)
+    z = run_case(g, dev, path)
+    assert z.shape == g["z"].shape and z.dtype == torch.float32 and z.is_cuda
+    assert rel_fro(z, g["z"]) <= TOL, name
+    assert support_mismatch(z.cpu(), g["z"]) <= 2e-3
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("init", ["zero", "ridge", "transpose"])
+def test_sparse_encode_inits(dev, init, path):
+    g = load_golden("encode_init_" + init)
+    z = sparse_encode(g["x"].to(dev), g["weight"].to(dev), alpha=g["alpha"], algorithm="ista",
+                      init=init, lr=g["lr"], maxiter=int(g["maxiter"]), tol=g["tol"], path=path)
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_early_stop_count_and_history(dev, path):
+    g = load_golden("ista_earlystop")
+    _, want_done, want_deltas = oracle.ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"],
+                                            fast=True, lr=g["lr"], maxiter=int(g["maxiter"]),
+                                            tol=g["tol"], return_info=True)
+    tol_abs = float(np.float32(g["z0"].numel() * g["tol"]))
+    z, done, hist = _cabi.fista_device(g["x"].to(dev), g["weight"].to(dev), None, g["alpha"],
+                                       g["lr"], int(g["maxiter"]), True, tol_abs, path=path,
+                                       want_iters=True, want_hist=True)
+    assert done == want_done
+    assert rel_fro(z, g["z"]) <= TOL
+    got = hist.cpu().numpy()[:want_done - 1]
+    np.testing.assert_allclose(got, np.array(want_deltas[:want_done - 1]), rtol=1e-4)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_host_entry_point_equals_device_entry_point(dev, path):
+    g = load_golden("ista_ragged")
+    zd = run_case(g, dev, path)
+    zh = ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=True, lr=g["lr"],
+              maxiter=int(g["maxiter"]), tol=g["tol"], path=path)
+    assert not zh.is_cuda
+    assert torch.equal(zh, zd.cpu())
+    pinned = g["x"].pin_memory()
+    zp = ista(pinned, g["z0"], g["weight"], alpha=g["alpha"], fast=True, lr=g["lr"],
+              maxiter=int(g["maxiter"]), tol=g["tol"], path=path)
+    assert torch.equal(zp, zh)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_edge_cases(dev, path):
+    x, w = make_problem(33, 7, 19, seed=2)
+    xd, wd = x.to(dev), w.to(dev)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    # maxiter = 0 through the C ABI copies the start
+    z0 = torch.rand(33, 19, device=dev)
+    z, done, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, 0, True, 0.0, path=path, want_iters=True)
+    assert done == 0 and torch.equal(z, z0)
+    z, _, _ = _cabi.fista_device(xd, wd, None, 0.1, lr, 0, True, 0.0, path=path)
+    assert float(z.abs().max()) == 0.0
+    # empty batch
+    ze = sparse_encode(xd[:0], wd, alpha=0.1, lr=lr, maxiter=5, path=path)
+    assert ze.shape == (0, 19)
+    # single row, single iteration, odd/even iteration counts land in the caller's buffer
+    for iters in (1, 2, 3, 4):
+        want = oracle.ista(x[:1], torch.zeros(1, 19), w, alpha=0.1, lr=lr, maxiter=iters, tol=0.0)
+        got = sparse_encode(xd[:1], wd, alpha=0.1, lr=lr, maxiter=iters, tol=0.0, path=path)
+        assert rel_fro(got, want) <= TOL
+    # result written in place over the start buffer (z_out aliases z0)
+    z0 = torch.zeros(33, 19, device=dev)
+    out, _, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, 7, True, 0.0, path=path, out=z0)
+    want = oracle.ista(x, torch.zeros(33, 19), w, alpha=0.1, lr=lr, maxiter=7, tol=0.0)
+    assert out.data_ptr() == z0.data_ptr() and rel_fro(z0, want) <= TOL
+    # all codes shrink to zero -> delta == 0 -> the stop test fires at the first iteration
+    z, done, _ = _cabi.fista_device(xd, wd, None, 1e3, lr, 9, True, 0.0, path=path, want_iters=True)
+    assert done == 1 and float(z.abs().max()) == 0.0
+    # non-contiguous inputs are accepted
+    xt = torch.randn(7, 33, device=dev).T
+    z = sparse_encode(xt, wd, alpha=0.1, lr=lr, maxiter=3, tol=0.0, path=path)
+    want = oracle.ista(xt.cpu().contiguous(), torch.zeros(33, 19), w, alpha=0.1, lr=lr, maxiter=3,
+                       tol=0.0)
+    assert rel_fro(z, want) <= TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_deterministic_and_shard_invariant(dev, path):
+    x, w = make_problem(4096, 64, 256, seed=0)
+    xd, wd = x.to(dev), w.to(dev)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    kw = dict(alpha=0.1, lr=lr, maxiter=40, tol=0.0, path=path)
+    full = sparse_encode(xd, wd, **kw)
+    again = sparse_encode(xd, wd, **kw)
+    assert torch.equal(full, again)
+    # rows are independent lasso problems: any row split gives the same bits
+    for shards in (2, 8, 3):
+        parts = [sparse_encode(part.contiguous(), wd, **kw) for part in xd.chunk(shards)]
+        assert torch.equal(torch.cat(parts), full)
+
+
+@pytest.mark.parametrize("kind", ["planted", "randn"])
+def test_full_size_c2_against_row_subset_oracle(dev, kind):
+    # BASELINE config 2: n=65536, d=64, k=256, alpha=0.1, 200 FISTA iterations, fp32
+    n, d, k, alpha, iters = 65536, 64, 256, 0.1, 200
+    x, w = make_problem(n, d, k, seed=0, kind=kind)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    z = sparse_encode(x.to(dev), w.to(dev), alpha=alpha, lr=lr, maxiter=iters, tol=0.0)
+    rows = torch.cat([torch.arange(0, 256), torch.arange(n // 2 - 100, n // 2 + 100),
+                      torch.arange(n - 256, n)])
+    want = oracle.ista(x[rows], torch.zeros(len(rows), k), w, alpha=alpha, lr=lr, maxiter=iters,
+                       tol=0.0)
+    got = z[rows.to(dev)].cpu()
+    assert rel_fro(got, want) <= TOL
+    assert support_mismatch(got, want) <= 2e-3
+    # size-independent property: one more ISTA step from the result barely moves it, and the
+    # objective is no worse than the oracle's on the subset
+    obj = lambda zz: float(oracle.lasso_loss(x[rows], zz, w, alpha))
+    assert obj(got) <= obj(want) * (1 + 1e-5)
+
+
+def test_kkt_conditions_after_convergence(dev):
+    x, w = make_problem(512, 32, 96, seed=4, kind="planted")
+    alpha = 0.05
+    z = sparse_encode(x.to(dev), w.to(dev), alpha=alpha, maxiter=3000, tol=0.0).cpu().double()
+    grad = (z @ w.double().T - x.double()) @ w.double()
+    on = z != 0
+    assert float((grad[on] + alpha * torch.sign(z[on])).abs().max()) <= 2e-5
+    assert float(grad[~on].abs().max()) <= alpha * (1 + 1e-4)
+
+
+@pytest.mark.parametrize("d,k", [(64, 256), (10, 50), (300, 40), (128, 1024), (1, 1)])
+def test_lipschitz_constant(dev, d, k):
+    w = torch.randn(d, k, generator=torch.Generator().manual_seed(d * k))
+    want = oracle.lipschitz_constant(w)
+    got = lipschitz_constant(w.to(dev))
+    assert abs(got - want) <= 1e-9 * want
+    assert abs(lipschitz_constant(w) - want) <= 1e-9 * want   # CPU tensor is moved, not solved on CPU
+
+
+def test_lr_auto_matches_pinned_lr(dev):
+    g = load_golden("ista_planted_200")
+    z = ista(g["x"].to(dev), g["z0"].to(dev), g["weight"].to(dev), alpha=g["alpha"],
+             maxiter=int(g["maxiter"]), tol=0.0)
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+def test_loss_and_statistics(dev):
+    g = load_golden("mstep")
+    x, z, w = g["x"].to(dev), g["z"].to(dev), g["weight"].to(dev)
+    loss = lasso_loss(x, z, w, g["alpha"])
+    assert loss.dtype == torch.float32 and abs(float(loss) - g["loss"]) <= 2e-6 * abs(g["loss"])
+    gzz, gzx = _cabi.gram(z, x)
+    z64, x64 = g["z"].double(), g["x"].double()
+    assert rel_fro(gzz, z64.T @ z64) <= 1e-6 and rel_fro(gzx, z64.T @ x64) <= 1e-6
+    # larger, ragged, sparse codes
+    xb, wb = make_problem(5000, 24, 70, seed=8)
+    zb = sparse_encode(xb.to(dev), wb.to(dev), alpha=0.1, maxiter=30, tol=0.0)
+    gzz, gzx = _cabi.gram(zb, xb.to(dev))
+    z64 = zb.cpu().double()
+    assert rel_fro(gzz, z64.T @ z64) <= 1e-6 and rel_fro(gzx, z64.T @ xb.double()) <= 1e-6
+    want = oracle.lasso_loss(xb, zb.cpu(), wb, 0.1)
+    assert abs(float(lasso_loss(xb.to(dev), zb, wb.to(dev), 0.1)) - float(want)) <= 1e-5 * float(want)
+
+
+def test_update_dict_matches_reference(dev):
+    g = load_golden("mstep")
+    w = g["weight"].to(dev).clone()
+    z = g["z"].to(dev).clone()
+    out = update_dict(w, g["x"].to(dev), z)
+    assert out.data_ptr() == w.data_ptr()          # in place, like the reference
+    assert rel_fro(w, g["weight_update"]) <= TOL
+    assert torch.equal(z.cpu(), g["z"])
+    v = update_dict_ridge(g["x"].to(dev), g["z"].to(dev), lambd=g["lambd"])
+    assert v.shape == g["weight_ridge"].shape and rel_fro(v, g["weight_ridge"]) <= TOL
+
+
+def test_update_dict_degenerate_atoms(dev):
+    g = load_golden("mstep_degenerate")
+    zero_atoms = [int(a) for a in g["zero_atoms"]]
+    w = g["weight"].to(dev).clone()
+    z = g["z"].to(dev).clone()
+    z[:, zero_atoms[0]] = 0
+    update_dict(w, g["x"].to(dev), z, random_seed=1234)
+    keep = [j for j in range(w.size(1)) if j not in zero_atoms]
+    assert rel_fro(w[:, keep], g["weight_update"][:, keep]) <= TOL
+    for j in zero_atoms:   # re-drawn atoms: unit norm, codes dropped
+        assert abs(float(w[:, j].norm()) - 1.0) <= 1e-6
+        assert float(z[:, j].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind", ["constrained", "ridge"])
+def test_dict_learning_matches_reference(dev, kind):
+    g = load_golden("dict_learning_" + kind)
+    torch.manual_seed(0)
+    w, losses = dict_learning(g["x"], 50, alpha=g["alpha"], constrained=(kind == "constrained"),
+                              steps=int(g["steps"]), lambd=g["lambd"], device="cpu", progbar=False,
+                              algorithm="ista", maxiter=int(g["maxiter"]))
+    assert w.shape == g["weight"].shape and not w.is_cuda and losses.shape == g["losses"].shape
+    assert torch.allclose(losses, g["losses"], rtol=2e-4)
+    assert rel_fro(w, g["weight"]) <= 5e-3
+    loss = dict_evaluate(g["x"].to(dev), w.to(dev), g["alpha"], maxiter=int(g["maxiter"]))
+    assert float(loss) == pytest.approx(float(oracle.lasso_loss(
+        g["x"], oracle.sparse_encode(g["x"], w, g["alpha"], maxiter=int(g["maxiter"])), w,
+        g["alpha"])), rel=1e-4)

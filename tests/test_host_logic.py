@@ -1,0 +1,147 @@
+"""Host-side logic of the drop-in boundary: argument handling, error behaviour of the
+reference API, the deferred global stop rule under a 2-rank gloo group.  CPU only:
+the CUDA calls are replaced by an oracle-backed stub where a result is needed."""
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import lasso_b200
+import oracle
+from lasso_b200.linear import initialize_code, sparse_encode
+from lasso_b200.linear.solvers import ista
+from lasso_b200.linear.solvers import ista as ista_fn
+from lasso_b200.testing import make_problem, rel_fro
+
+ista_mod = __import__("sys").modules["lasso_b200.linear.solvers.ista"]
+
+
+def test_api_surface_matches_reference_names():
+    lin = lasso_b200.linear
+    for name in ("sparse_encode", "initialize_code", "dict_learning", "dict_evaluate",
+                 "update_dict", "update_dict_ridge", "solvers", "utils"):
+        assert hasattr(lin, name)
+    import inspect
+    sig = inspect.signature(ista_fn)
+    want = [("alpha", 1.0), ("fast", True), ("lr", 'auto'), ("maxiter", 10), ("tol", 1e-5),
+            ("backtrack", False), ("eta_backtrack", 1.5), ("verbose", False)]
+    names = list(sig.parameters)
+    assert names[:3] == ["x", "z0", "weight"]
+    for key, default in want:
+        assert sig.parameters[key].default == default
+    sig = inspect.signature(lin.sparse_encode)
+    assert list(sig.parameters)[:6] == ["x", "weight", "alpha", "z0", "algorithm", "init"]
+    sig = inspect.signature(lin.dict_learning)
+    assert list(sig.parameters)[:9] == ["X", "n_components", "alpha", "constrained", "persist",
+                                        "lambd", "steps", "device", "progbar"]
+    assert sig.parameters["steps"].default == 60 and sig.parameters["lambd"].default == 1e-2
+
+
+def test_error_behaviour_of_the_reference_is_kept():
+    x, w = torch.randn(6, 4), torch.randn(4, 5)
+    with pytest.raises(ValueError, match="invalid algorithm parameter 'nope'"):
+        sparse_encode(x, w, algorithm="nope")
+    with pytest.raises(ValueError, match="invalid init parameter 'bogus'"):
+        sparse_encode(x, w, init="bogus")
+    with pytest.raises(AssertionError):
+        sparse_encode(x, w, z0=torch.zeros(6, 4))
+    with pytest.raises(ValueError, match="eta must be > 1"):
+        ista(x, torch.zeros(6, 5), w, lr=0.1, backtrack=True, eta_backtrack=1.0)
+    with pytest.raises(NotImplementedError):
+        sparse_encode(x, w, algorithm="cd")
+    with pytest.raises(NotImplementedError):
+        sparse_encode(x.double(), w.double(), lr=0.1)
+    z0 = torch.zeros(6, 5)
+    assert ista(x, z0, w, lr=0.1, maxiter=0) is z0      # the reference returns z0 itself
+
+
+def test_initialize_code_modes():
+    x, w = make_problem(12, 5, 9, seed=1)
+    assert torch.equal(initialize_code(x, w, 0.3, "zero"), torch.zeros(12, 9))
+    u = initialize_code(x, w, 0.3, "unif")
+    assert u.shape == (12, 9) and float(u.abs().max()) <= 0.1
+    assert rel_fro(initialize_code(x, w, 0.3, "transpose"), x @ w) == 0
+    assert rel_fro(initialize_code(x, w, 0.3, "ridge"),
+                   oracle.initialize_code(x, w, 0.3, "ridge")) <= 1e-5
+
+
+def test_momentum_schedule_and_tolerance_helpers():
+    betas = oracle.beta_schedule(5)
+    assert betas[0] == 0.0
+    t1 = (1 + math.sqrt(5)) / 2
+    assert betas[1] == pytest.approx((t1 - 1) / ((1 + math.sqrt(1 + 4 * t1 * t1)) / 2))
+    assert ista_mod._abs_tolerance(65536 * 256, 1e-5) == pytest.approx(167.77216, rel=1e-6)
+    hist = torch.tensor([5.0, 3.0, 0.5, 0.4, 0.1], dtype=torch.float64)
+    assert ista_mod._first_stop(hist, 1.0) == 3
+    assert ista_mod._first_stop(hist, 0.01) == 5
+    assert ista_mod._first_stop(hist, 0.1) == 5   # the last iteration never "stops early"
+
+
+# ---------------------------------------------------------------------------------------
+# 2-rank gloo: the deferred, all-reduced stop rule must reproduce the unsharded result
+# ---------------------------------------------------------------------------------------
+
+def _oracle_backed_fista_device(x, weight, z0, alpha, lr, maxiter, fast, tol_abs, path=0,
+                                want_iters=False, want_hist=False, out=None):
+    n, k = x.shape[0], weight.shape[1]
+    start = z0 if z0 is not None else torch.zeros(n, k)
+    tol = -1.0 if tol_abs < 0 else tol_abs / max(start.numel(), 1)
+    z, done, deltas = oracle.ista(x, start, weight, alpha=alpha, fast=bool(fast), lr=lr,
+                                  maxiter=maxiter, tol=tol, return_info=True)
+    hist = torch.zeros(maxiter, dtype=torch.float64)
+    hist[:len(deltas)] = torch.tensor(deltas, dtype=torch.float64)
+    return z, (done if want_iters else None), (hist if want_hist else None)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _sharded_worker(rank, world, port, tol, maxiter, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import lasso_b200 as pkg
+        mod = __import__("sys").modules["lasso_b200.linear.solvers.ista"]
+        pkg._cabi.fista_device = _oracle_backed_fista_device
+        x, w = make_problem(64, 16, 32, seed=len("ista_earlystop"), kind="planted")
+        lr = 1.0 / oracle.lipschitz_constant(w)
+        rows = slice(rank * 32, (rank + 1) * 32)
+        xs = x[rows].clone()
+        # pretend the shard is a CUDA tensor for the host logic only
+        class Shard(torch.Tensor):
+            @property
+            def is_cuda(self):
+                return True
+        xs = xs.as_subclass(Shard)
+        z, done = mod.solve(xs, None, w, alpha=0.1, fast=True, lr=lr, maxiter=maxiter, tol=tol,
+                            group=dist.group.WORLD, return_iters=True)
+        torch.save({"z": torch.Tensor(z), "done": done}, os.path.join(result_dir, "r%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tol,maxiter", [(1e-3, 500), (0.0, 40)])
+def test_sharded_stop_rule_two_ranks(tmp_path, tol, maxiter):
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(2, port, tol, maxiter, str(tmp_path)), nprocs=2, join=True)
+    x, w = make_problem(64, 16, 32, seed=len("ista_earlystop"), kind="planted")
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    want, want_done, _ = oracle.ista(x, torch.zeros(64, 32), w, alpha=0.1, fast=True, lr=lr,
+                                     maxiter=maxiter, tol=tol, return_info=True)
+    parts = [torch.load(os.path.join(str(tmp_path), "r%d.pt" % r)) for r in range(2)]
+    got = torch.cat([p["z"] for p in parts])
+    assert parts[0]["done"] == parts[1]["done"] == want_done
+    if tol > 0:
+        assert want_done < maxiter
+    # rows are independent: the sharded run equals the unsharded one bit for bit
+    assert torch.equal(got, want)

@@ -1,0 +1,106 @@
+"""The oracle (oracle/ista_oracle.py) against the golden vectors produced by the real
+reference (tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+import oracle
+from conftest import SOLVER_CASES, load_golden
+from lasso_b200.testing import rel_fro
+
+# Same torch build + same machine gives bit-identical results; a different CPU can
+# select other MKL kernels, so allow float32 summation-order noise.
+TOL = 2e-6
+
+
+@pytest.mark.parametrize("name", SOLVER_CASES)
+def test_ista_matches_reference(name):
+    g = load_golden(name)
+    z = oracle.ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=bool(g["fast"]),
+                    lr=g["lr"], maxiter=int(g["maxiter"]), tol=g["tol"])
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+def test_backtracking_matches_reference():
+    g = load_golden("ista_backtrack")
+    z = oracle.ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=True, lr=g["lr"],
+                    maxiter=int(g["maxiter"]), tol=g["tol"], backtrack=True,
+                    eta_backtrack=g["eta_backtrack"])
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+@pytest.mark.parametrize("init", ["zero", "ridge", "transpose"])
+def test_initialize_code(init):
+    g = load_golden("encode_init_" + init)
+    z0 = oracle.initialize_code(g["x"], g["weight"], g["alpha"], init)
+    assert rel_fro(z0, g["z0"]) <= TOL
+    z = oracle.sparse_encode(g["x"], g["weight"], g["alpha"], init=init, lr=g["lr"],
+                             maxiter=int(g["maxiter"]), tol=g["tol"])
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+def test_early_stop_iteration_count():
+    g = load_golden("ista_earlystop")
+    z, done, deltas = oracle.ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=True,
+                                  lr=g["lr"], maxiter=int(g["maxiter"]), tol=g["tol"],
+                                  return_info=True)
+    assert 1 < done < int(g["maxiter"])          # the stop test fired
+    assert deltas[-1] <= g["z0"].numel() * g["tol"] < deltas[-2]
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+def test_f64_gold_close_to_reference():
+    g = load_golden("ista_planted_200")
+    z64 = oracle.ista_f64(g["x"].numpy(), g["z0"].numpy(), g["weight"].numpy(), g["alpha"],
+                          g["lr"], int(g["maxiter"]))
+    # the float32 reference sits 5e-7..3e-6 from the float64 solution
+    assert rel_fro(torch.from_numpy(z64), g["z"]) <= 1e-5
+
+
+def test_mstep_matches_reference():
+    g = load_golden("mstep")
+    assert abs(float(oracle.lasso_loss(g["x"], g["z"], g["weight"], g["alpha"])) - g["loss"]) \
+        <= 1e-6 * abs(g["loss"])
+    w = oracle.update_dict(g["weight"].clone(), g["x"], g["z"].clone())
+    assert rel_fro(w, g["weight_update"]) <= TOL
+    w = oracle.update_dict_ridge(g["x"], g["z"], lambd=g["lambd"])
+    assert rel_fro(w, g["weight_ridge"]) <= 1e-5
+
+
+def test_gram_space_sweep_equals_sequential_sweep():
+    g = load_golden("mstep")
+    z64, x64 = g["z"].double(), g["x"].double()
+    w, zeroed = oracle.update_dict_gram(g["weight"], z64.T @ z64, z64.T @ x64)
+    assert zeroed == []
+    assert rel_fro(w, g["weight_update"]) <= 5e-6
+
+
+def test_degenerate_atoms():
+    g = load_golden("mstep_degenerate")
+    zero_atoms = [int(a) for a in g["zero_atoms"]]
+    torch.manual_seed(1234)
+    w = oracle.update_dict(g["weight"].clone(), g["x"], g["z"].clone())
+    assert rel_fro(w, g["weight_update"]) <= TOL
+    z64, x64 = g["z"].double(), g["x"].double()
+    w2, zeroed = oracle.update_dict_gram(g["weight"], z64.T @ z64, z64.T @ x64)
+    assert zeroed == zero_atoms
+    keep = [j for j in range(w.size(1)) if j not in zero_atoms]
+    assert rel_fro(w2[:, keep], g["weight_update"][:, keep]) <= 5e-6
+
+
+@pytest.mark.parametrize("kind", ["constrained", "ridge"])
+def test_dict_learning_matches_reference(kind):
+    g = load_golden("dict_learning_" + kind)
+    w, losses = oracle.dict_learning(g["x"], g["weight0"].size(1), alpha=g["alpha"],
+                                     constrained=(kind == "constrained"), steps=int(g["steps"]),
+                                     lambd=g["lambd"], weight0=g["weight0"],
+                                     maxiter=int(g["maxiter"]))
+    # lr='auto' differs (ARPACK float32 vs float64 eigvalsh): 1e-6 on lr, amplified by EM
+    assert torch.allclose(losses, g["losses"], rtol=2e-4)
+    assert rel_fro(w, g["weight"]) <= 5e-3
+
+
+def test_dict_learning_init_draw_is_the_references():
+    g = load_golden("dict_learning_constrained")
+    torch.manual_seed(0)
+    w, _ = oracle.dict_learning(g["x"], 50, alpha=g["alpha"], steps=0)
+    assert torch.equal(w, g["weight0"])
