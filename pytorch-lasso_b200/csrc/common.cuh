@@ -52,7 +52,10 @@ struct StepCtl {
 // ---- device helpers ---------------------------------------------------------
 __device__ __forceinline__ float soft_threshold(float v, float lam) {
   // ATen softshrink: v > lam ? v - lam : (v < -lam ? v + lam : 0)   (ista.py:90)
-  return v > lam ? __fsub_rn(v, lam) : (v < -lam ? __fadd_rn(v, lam) : 0.0f);
+  // Branch-free and bit-identical: v + lam == -(|v| - lam) exactly for v < -lam, the
+  // result is +0 inside the dead zone and for NaN (both comparisons false), like ATen's.
+  const float mag = fmaxf(__fsub_rn(fabsf(v), lam), 0.0f);
+  return mag > 0.0f ? copysignf(mag, v) : 0.0f;
 }
 
 __device__ __forceinline__ float momentum_point(float zc, float zp, float beta) {

@@ -39,22 +39,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  // potentially-blocking test: the hardware may suspend the thread up to the hinted time
+  // (ns) and wakes it when the phase completes, so waiting warps stop burning issue slots
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  Returns false on timeout.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity,
-                                          uint32_t max_spins = 1u << 24) {
-  for (uint32_t i = 0; i < max_spins; ++i)
+// Bounded wait: a protocol bug must not hang the GPU.  Returns false after ~2 s.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = global_timer_ns();
+  for (;;) {
     if (mbar_try_wait(bar, parity)) return true;
-  return false;
+    if (global_timer_ns() - t0 > 2000000000ull) return false;
+  }
 }
 
 // ------------------------------------------------------------------ fences --

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128) probe_kernel(ProbeArgs p) {
     mma_commit(&bar);
   }
   __syncwarp();
-  const bool ok = mbar_wait(&bar, 0, 1u << 22);
+  const bool ok = mbar_wait(&bar, 0);
   tc_fence_after();
   if (!ok) {
     if (lane == 0) atomicExch(p.status, 1);
