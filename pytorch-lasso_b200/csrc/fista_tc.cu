@@ -68,25 +68,52 @@ struct TcParams {
   int cur_is_a;            // which tensor map holds z_cur
   StepCtl ctl;
   volatile int* dbg;       // host-mapped debug record or nullptr
+  unsigned long long* trace;  // LASSO_B200_TRACE: per-warp (clock << 8 | event) log of block 0
 };
 
-// A barrier that does not complete is a protocol bug: record where (host-mapped debug
-// record, if armed with LASSO_B200_DEBUG=1) and trap instead of hanging the GPU.
-#define TC_WAIT(bar, parity)                                              \
-  do {                                                                    \
-    if (p.dbg) p.dbg[64 + blockIdx.x * 16 + (threadIdx.x >> 5)] = __LINE__ * 16 + (int)(parity); \
-    if (!mbar_wait((bar), (parity))) {                                    \
-      if (p.dbg) {                                                        \
-        p.dbg[64 + blockIdx.x * 16 + (threadIdx.x >> 5)] = -(__LINE__ * 16 + (int)(parity)); \
-        p.dbg[1] = __LINE__; p.dbg[2] = blockIdx.x; p.dbg[3] = threadIdx.x; \
-        p.dbg[4] = p.ctl.iter; p.dbg[5] = (int)(parity);                  \
-        __threadfence_system();                                           \
-        p.dbg[0] = 1;                                                     \
-        __threadfence_system();                                           \
-      }                                                                   \
-      __trap();                                                           \
-    }                                                                     \
-    if (p.dbg) p.dbg[64 + blockIdx.x * 16 + (threadIdx.x >> 5)] = 0;      \
+// A barrier that does not complete is a protocol bug: after ~2 s record where (host-mapped
+// debug record, armed with LASSO_B200_DEBUG=1) and trap instead of hanging the GPU.
+__device__ __noinline__ void tc_wait_slow_path(uint64_t& t0, volatile int* dbg, int line, int iter,
+                                               uint32_t parity) {
+  const uint64_t now = global_timer_ns();
+  if (t0 == 0) {
+    t0 = now;
+    return;
+  }
+  if (now - t0 < 2000000000ull) return;
+  if (dbg) {
+    dbg[1] = line; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x; dbg[4] = iter; dbg[5] = (int)parity;
+    __threadfence_system();
+    dbg[0] = 1;
+    __threadfence_system();
+  }
+  __trap();
+}
+// The polling loop is spelled out in the macro (not an inline function) so that profiler
+// samples of a wait land on the line of the wait, i.e. tell WHICH barrier a warp sat on.
+#define TC_WAIT(bar, parity)                                                              \
+  do {                                                                                    \
+    const uint32_t _addr = smem_u32(bar), _par = (parity);                                \
+    uint32_t _ok, _n = 0;                                                                 \
+    uint64_t _t0 = 0;                                                                     \
+    for (;;) {                                                                            \
+      asm volatile(                                                                       \
+          "{\n\t.reg .pred P;\n\t"                                                       \
+          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"                  \
+          "selp.b32 %0, 1, 0, P;\n\t}\n"                                                   \
+          : "=r"(_ok)                                                                     \
+          : "r"(_addr), "r"(_par), "r"(20000u)                                            \
+          : "memory");                                                                    \
+      if (_ok) break;                                                                     \
+      if ((++_n & 1023u) == 0) tc_wait_slow_path(_t0, p.dbg, __LINE__, p.ctl.iter, _par); \
+    }                                                                                     \
+  } while (0)
+
+// timeline instrumentation (block 0, lane 0 of every warp), enabled with LASSO_B200_TRACE=<file>
+#define TRACE(id)                                                                         \
+  do {                                                                                    \
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < 510)   \
+      p.trace[(threadIdx.x >> 5) * 512 + tr_n++] = ((unsigned long long)clock64() << 8) | (id); \
   } while (0)
 
 // exact three-way bf16 split of an fp32 value: v = p1 + p2 + p3 (upper 16 bits each)
@@ -100,6 +127,37 @@ __device__ __forceinline__ void split3(float v, uint32_t& p1, uint32_t& p2, uint
 // two bf16 (upper halves of a, b) -> one 32-bit word, element a in the low half
 __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) {
   return __byte_perm(a, b, 0x7632);
+}
+
+// named barrier of one compute group (4 warps); ids 2 and 3 (0 = __syncthreads, 1 = all compute)
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot per pair.
+// a - b is formed as fma(-1, b, a): a single rounding of the exact difference, i.e. the
+// same bits as __fsub_rn, so the reference's rounding sequence is preserved.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  return __ffma2_rn(make_float2(-1.f, -1.f), b, a);
+}
+// pair version of split3: packed words of the three bf16 pieces of (v.x, v.y)
+__device__ __forceinline__ void split3_pair(float2 v, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  const float2 t1 = make_float2(__uint_as_float(__float_as_uint(v.x) & 0xFFFF0000u),
+                                __uint_as_float(__float_as_uint(v.y) & 0xFFFF0000u));
+  const float2 r1 = sub2(v, t1);
+  const float2 t2 = make_float2(__uint_as_float(__float_as_uint(r1.x) & 0xFFFF0000u),
+                                __uint_as_float(__float_as_uint(r1.y) & 0xFFFF0000u));
+  const float2 r2 = sub2(r1, t2);
+  w1 = pack_hi(__float_as_uint(t1.x), __float_as_uint(t1.y));
+  w2 = pack_hi(__float_as_uint(t2.x), __float_as_uint(t2.y));
+  w3 = pack_hi(__float_as_uint(r2.x), __float_as_uint(r2.y));
+}
+// softshrink(y - lr*g, lam) on a pair: v - clamp(v, -lam, lam) is bit-identical to ATen's
+// three-way select for finite v (v - lam, v + lam or +0 with one rounding each).
+__device__ __forceinline__ float2 ista_update_pair(float2 y, float2 g, float2 lr2, float lam) {
+  const float2 v = sub2(y, __fmul2_rn(lr2, g));
+  const float2 c = make_float2(fminf(fmaxf(v.x, -lam), lam), fminf(fmaxf(v.y, -lam), lam));
+  return sub2(v, c);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -116,6 +174,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   if (p.ctl.tol_abs >= 0.0 && p.ctl.iter >= 2 && p.ctl.hist[p.ctl.iter - 2] <= p.ctl.tol_abs) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tr_n = 0;
   const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
   const int nc = (p.k + kChunk - 1) / kChunk;   // phase-A chunks
   const int nq = (p.k + kQ - 1) / kQ;           // GEMM2 chunks
@@ -150,96 +209,133 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       prefetch_tmap(&tm_za);
       prefetch_tmap(&tm_zb);
       mbar_expect_tx(&bar_w, kWBytes);
       for (uint32_t off = 0; off < kWBytes; off += 16384)
         bulk_load(smem + kSmemW + off, p.w_image + off, 16384, &bar_w);
-      // Chunk c belongs to compute group c & 1, and each group owns its own two-stage ring
-      // (stages g and g + 2).  One consumer group per barrier keeps every waiter within one
-      // phase of the barrier, which is all a parity wait can disambiguate.
-      uint32_t m[2] = {0, 0};
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row0 = (int)(tile * kTileM);
-        for (int c = 0; c < nc; ++c) {
-          const int g = c & 1;
-          const uint32_t s = g + 2 * (m[g] & 1), ph = (m[g] >> 1) & 1;
-          ++m[g];
-          TC_WAIT(&bar_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    // Chunk c belongs to compute group c & 1, and each group owns its own two-stage ring
+    // (stages g and g + 2).  One consumer group per barrier keeps every waiter within one
+    // phase of the barrier, which is all a parity wait can disambiguate.
+    uint32_t m0 = 0, m1 = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int row0 = (int)(tile * kTileM);
+      for (int c = 0; c < nc; ++c) {
+        const int g = c & 1;
+        const uint32_t mg = g ? m1 : m0;
+        const uint32_t s = g + 2 * (mg & 1), ph = (mg >> 1) & 1;
+        if (g) ++m1; else ++m0;
+        TC_WAIT(&bar_empty[s], ph ^ 1);
+        TRACE(1);
+        if (elect_one()) {
           mbar_expect_tx(&bar_full[s], kStageBytes);
           uint8_t* dst = smem + kSmemStage + s * kStageBytes;
           tma_load_2d(dst, tm_cur, c * kChunk, row0, &bar_full[s]);
           tma_load_2d(dst + kBoxBytes, tm_prev, c * kChunk, row0, &bar_full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(kFmtBF16, 128, kDP, 0, 0);   // B K-major  (GEMM1)
-      const uint32_t idesc2 = make_idesc(kFmtBF16, 128, kQ, 0, 1);    // B MN-major (GEMM2)
-      const uint32_t w_addr = smem_u32(smem + kSmemW);
-      TC_WAIT(&bar_w, 0);
-      uint32_t a_cnt[2] = {0, 0}, g_cnt[2] = {0, 0}, ti = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-        // accumulators alias the G buffers of the previous tile: wait until both were drained
-        TC_WAIT(&bar_gfree[0], (g_cnt[0] & 1) ^ 1);
-        TC_WAIT(&bar_gfree[1], (g_cnt[1] & 1) ^ 1);
+    // The whole warp runs this control flow (every value is warp-uniform); only the
+    // tcgen05.mma / commit instructions sit under elect_one(), so the descriptors live in
+    // uniform registers and one MMA costs a handful of issue slots.
+    const uint32_t idesc1 = make_idesc(kFmtBF16, 128, kDP, 0, 0);   // B K-major  (GEMM1)
+    const uint32_t idesc2 = make_idesc(kFmtBF16, 128, kQ, 0, 1);    // B MN-major (GEMM2)
+    const uint32_t w_addr = smem_u32(smem + kSmemW);
+    // descriptor of piece 0 / offset 0 in both views; per MMA only the low word moves
+    const uint64_t desc1 = make_smem_desc_sw128(w_addr, 0, 1024);
+    const uint64_t desc2 = make_smem_desc_sw128(w_addr, kSlabBytes, 1024);
+    const uint32_t d1_lo = (uint32_t)desc1, d1_hi = (uint32_t)(desc1 >> 32);
+    const uint32_t d2_lo = (uint32_t)desc2, d2_hi = (uint32_t)(desc2 >> 32);
+    constexpr uint32_t kPiece16 = kPieceBytes >> 4;   // descriptor address units (16 B)
+    auto make64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    TC_WAIT(&bar_w, 0);
+    uint32_t a_cnt0 = 0, a_cnt1 = 0, g_cnt0 = 0, g_cnt1 = 0, ti = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      // accumulators alias the G buffers of the previous tile: wait until both were drained
+      TC_WAIT(&bar_gfree[0], (g_cnt0 & 1) ^ 1);
+      TC_WAIT(&bar_gfree[1], (g_cnt1 & 1) ^ 1);
+      TRACE(10);
+      tc_fence_after();
+      // ---- GEMM1: R[128 x 64] = Y[128 x k] * W^T ----
+      for (int c = 0; c < nc; ++c) {
+        const int b = c & 1;
+        if (b == 0) {
+          TC_WAIT(&bar_aready[0], a_cnt0 & 1);
+          ++a_cnt0;
+        } else {
+          TC_WAIT(&bar_aready[1], a_cnt1 & 1);
+          ++a_cnt1;
+        }
+        TRACE(11);
         tc_fence_after();
-        // ---- GEMM1: R[128 x 64] = Y[128 x k] * W^T ----
-        for (int c = 0; c < nc; ++c) {
-          const int b = c & 1;
-          TC_WAIT(&bar_aready[b], a_cnt[b] & 1);
-          ++a_cnt[b];
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t t_stage = tbase + kColStage + b * 48;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t koff = (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)((c & 1) * 32 + ks * 16) * 2;
+            // 64-atom slab (c >> 1), 16 atoms per k-step, 2 bytes each -> units of 16 B
+            const uint32_t koff = (uint32_t)(c >> 1) * (kSlabBytes >> 4) + (uint32_t)((c & 1) * 4 + ks * 2);
             const uint32_t acc_on = (c > 0 || ks > 0) ? 1u : 0u;
-            auto bdesc = [&](int piece) {
-              return make_smem_desc_sw128(w_addr + piece * kPieceBytes + koff, 0, 1024);
-            };
-            auto aaddr = [&](int piece) { return t_stage + piece * 16 + ks * 8; };
-            // small products (p1 q2, p2 q1, p1 q3, p2 q2, p3 q1) -> R_small
-            mma_ts<false>(tbase + kColAcc1, aaddr(0), bdesc(2), idesc1, acc_on);
-            mma_ts<false>(tbase + kColAcc1, aaddr(1), bdesc(1), idesc1, 1);
-            mma_ts<false>(tbase + kColAcc1, aaddr(2), bdesc(0), idesc1, 1);
-            mma_ts<false>(tbase + kColAcc1, aaddr(0), bdesc(1), idesc1, 1);
-            mma_ts<false>(tbase + kColAcc1, aaddr(1), bdesc(0), idesc1, 1);
+            const uint64_t q1 = make64(d1_lo + koff, d1_hi);
+            const uint64_t q2 = make64(d1_lo + koff + kPiece16, d1_hi);
+            const uint64_t q3 = make64(d1_lo + koff + 2 * kPiece16, d1_hi);
+            const uint32_t p1 = t_stage + ks * 8, p2 = p1 + 16, p3 = p1 + 32;
+            // small products (p1 q3, p2 q2, p3 q1, p1 q2, p2 q1) -> R_small
+            mma_ts<false>(tbase + kColAcc1, p1, q3, idesc1, acc_on);
+            mma_ts<false>(tbase + kColAcc1, p2, q2, idesc1, 1);
+            mma_ts<false>(tbase + kColAcc1, p3, q1, idesc1, 1);
+            mma_ts<false>(tbase + kColAcc1, p1, q2, idesc1, 1);
+            mma_ts<false>(tbase + kColAcc1, p2, q1, idesc1, 1);
             // leading product -> R_big
-            mma_ts<false>(tbase + kColAcc0, aaddr(0), bdesc(0), idesc1, acc_on);
+            mma_ts<false>(tbase + kColAcc0, p1, q1, idesc1, acc_on);
           }
           mma_commit(&bar_sfree[b]);
+          if (c == nc - 1) mma_commit(&bar_rfull);
         }
-        mma_commit(&bar_rfull);
-        // ---- GEMM2: G[128 x 64q] = r[128 x d] * W[:, chunk] ----
-        TC_WAIT(&bar_rready, ti & 1);
+        __syncwarp();
+        TRACE(12);
+      }
+      // ---- GEMM2: G[128 x 64q] = r[128 x d] * W[:, chunk] ----
+      TC_WAIT(&bar_rready, ti & 1);
+      TRACE(14);
+      tc_fence_after();
+      for (int q = 0; q < nq; ++q) {
+        const int b = q & 1;
+        if (b == 0) {
+          TC_WAIT(&bar_gfree[0], (g_cnt0 & 1) ^ 1);
+          ++g_cnt0;
+        } else {
+          TC_WAIT(&bar_gfree[1], (g_cnt1 & 1) ^ 1);
+          ++g_cnt1;
+        }
+        TRACE(15);
         tc_fence_after();
-        for (int q = 0; q < nq; ++q) {
-          const int b = q & 1;
-          TC_WAIT(&bar_gfree[b], (g_cnt[b] & 1) ^ 1);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t t_acc = tbase + (b ? kColAcc1 : kColAcc0);
-          auto bdesc = [&](int piece, int ks) {
-            return make_smem_desc_sw128(w_addr + piece * kPieceBytes + q * kSlabBytes + ks * 2048,
-                                        kSlabBytes, 1024);
-          };
-          auto aaddr = [&](int piece, int ks) { return tbase + kColStage + piece * 32 + ks * 8; };
+          const uint32_t t_r = tbase + kColStage;
+          const uint32_t qoff = (uint32_t)q * (kSlabBytes >> 4);
           uint32_t acc_on = 0;
-          // small products first (their truncation error scales with a small accumulator)
-          const int pa[5] = {2, 1, 0, 1, 0}, pb[5] = {0, 1, 2, 0, 1};
+          // small products first (their truncation error scales with a small accumulator):
+          // (r3 q1) (r2 q2) (r1 q3) (r2 q1) (r1 q2), leading (r1 q1) last
 #pragma unroll
-          for (int t = 0; t < 5; ++t)
+          for (int t = 0; t < 6; ++t) {
+            constexpr int pa[6] = {2, 1, 0, 1, 0, 0}, pb[6] = {0, 1, 2, 0, 1, 0};
             for (int ks = 0; ks < dsteps; ++ks) {
-              mma_ts<false>(t_acc, aaddr(pa[t], ks), bdesc(pb[t], ks), idesc2, acc_on);
+              // 16 k-rows of 128 B per k-step = 2048 B = 128 units
+              const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
+              mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
               acc_on = 1;
             }
-          for (int ks = 0; ks < dsteps; ++ks) mma_ts<false>(t_acc, aaddr(0, ks), bdesc(0, ks), idesc2, 1);
+          }
           mma_commit(&bar_gfull[b]);
-          ++g_cnt[b];
         }
+        __syncwarp();
+        TRACE(16);
       }
     }
   } else {
@@ -249,50 +345,57 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     double dsum = 0.0;
+    const float2 lr2 = make_float2(p.lr, p.lr);
+    const bool has_out = nq > grp;   // this group owns at least one GEMM2 chunk per tile
     uint32_t a_cnt = 0, g_cnt = 0, ti = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int64_t grow = tile * kTileM + row;
+      uint32_t keep_stage = grp;   // set in phase A whenever has_out
+      // pull this thread's 128-byte slice of x towards L2 now; phase B reads it ~10k cycles later
+      if (grow < p.n && grp * 32 < p.d)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + grow * p.d + grp * 32));
       // ---------------- phase A ----------------
       for (int c = grp; c < nc; c += 2) {
         // a_cnt = chunks this group consumed so far = index into its private stage ring
         const uint32_t s = grp + 2 * (a_cnt & 1), ph = (a_cnt >> 1) & 1;
         TC_WAIT(&bar_full[s], ph);
+        TRACE(20);
         const uint8_t* zc_s = smem + kSmemStage + s * kStageBytes;
         const uint8_t* zp_s = zc_s + kBoxBytes;
-        float y[kChunk];
+        // y = z_cur + beta (z_cur - z_prev) on fp32 pairs; |z_cur - z_prev| feeds the lagged
+        // stop-test sum; then the exact three-way bf16 split of every y
+        uint32_t yb[kChunk], w1[16], w2[16], w3[16];
         float part = 0.f;
+        const float2 beta2 = make_float2(p.beta, p.beta);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t off = sw128_offset(row, j * 16);
           const float4 zc = *reinterpret_cast<const float4*>(zc_s + off);
+          float2 ya = make_float2(zc.x, zc.y), yc = make_float2(zc.z, zc.w);
           if (p.use_prev) {
             const float4 zp = *reinterpret_cast<const float4*>(zp_s + off);
-            y[4 * j + 0] = momentum_point(zc.x, zp.x, p.beta);
-            y[4 * j + 1] = momentum_point(zc.y, zp.y, p.beta);
-            y[4 * j + 2] = momentum_point(zc.z, zp.z, p.beta);
-            y[4 * j + 3] = momentum_point(zc.w, zp.w, p.beta);
-            part += fabsf(__fsub_rn(zp.x, zc.x)) + fabsf(__fsub_rn(zp.y, zc.y)) +
-                    fabsf(__fsub_rn(zp.z, zc.z)) + fabsf(__fsub_rn(zp.w, zc.w));
-          } else {
-            y[4 * j + 0] = zc.x; y[4 * j + 1] = zc.y; y[4 * j + 2] = zc.z; y[4 * j + 3] = zc.w;
+            const float2 da = sub2(ya, make_float2(zp.x, zp.y));
+            const float2 dc = sub2(yc, make_float2(zp.z, zp.w));
+            part += (fabsf(da.x) + fabsf(da.y)) + (fabsf(dc.x) + fabsf(dc.y));
+            ya = __fadd2_rn(ya, __fmul2_rn(beta2, da));
+            yc = __fadd2_rn(yc, __fmul2_rn(beta2, dc));
           }
+          yb[4 * j + 0] = __float_as_uint(ya.x);
+          yb[4 * j + 1] = __float_as_uint(ya.y);
+          yb[4 * j + 2] = __float_as_uint(yc.x);
+          yb[4 * j + 3] = __float_as_uint(yc.y);
+          split3_pair(ya, w1[2 * j], w2[2 * j], w3[2 * j]);
+          split3_pair(yc, w1[2 * j + 1], w2[2 * j + 1], w3[2 * j + 1]);
         }
-        mbar_arrive(&bar_empty[s]);   // stage consumed (values are in registers)
+        // stage consumed (values are in registers).  The last stage of the tile is withheld:
+        // phase C stages its output there and releases it afterwards.
+        if (has_out && c + 2 >= nc) keep_stage = s;
+        else mbar_arrive(&bar_empty[s]);
         dsum += (double)part;
-        uint32_t yb[kChunk], w1[16], w2[16], w3[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          uint32_t a1, a2, a3, b1, b2, b3;
-          split3(y[2 * j], a1, a2, a3);
-          split3(y[2 * j + 1], b1, b2, b3);
-          w1[j] = pack_hi(a1, b1);
-          w2[j] = pack_hi(a2, b2);
-          w3[j] = pack_hi(a3, b3);
-          yb[2 * j] = __float_as_uint(y[2 * j]);
-          yb[2 * j + 1] = __float_as_uint(y[2 * j + 1]);
-        }
         // the piece stage is free once the MMAs of its previous chunk completed
+        TRACE(21);
         TC_WAIT(&bar_sfree[grp], (a_cnt & 1) ^ 1);
+        TRACE(22);
         ++a_cnt;
         tc_fence_after();
         tmem_st32(tbase + lane_base + kColY + c * kChunk, yb);
@@ -303,6 +406,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bar_aready[grp]);
+        TRACE(23);
       }
       // ---------------- phase B: r = R - x, pieces of r ----------------
       {
@@ -317,6 +421,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
             xv[j] = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.d + col));
         }
         TC_WAIT(&bar_rfull, ti & 1);
+        TRACE(30);
         tc_fence_after();
         uint32_t rb[32], rs[32];
         tmem_ld32(tbase + lane_base + kColAcc0 + grp * 32, rb);
@@ -325,19 +430,15 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         uint32_t w1[16], w2[16], w3[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xr[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
-          float r[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            r[e] = __fsub_rn(__fadd_rn(__uint_as_float(rb[4 * j + e]), __uint_as_float(rs[4 * j + e])),
-                             xr[e]);
-          uint32_t a1, a2, a3, b1, b2, b3;
-          split3(r[0], a1, a2, a3);
-          split3(r[1], b1, b2, b3);
-          w1[2 * j] = pack_hi(a1, b1); w2[2 * j] = pack_hi(a2, b2); w3[2 * j] = pack_hi(a3, b3);
-          split3(r[2], a1, a2, a3);
-          split3(r[3], b1, b2, b3);
-          w1[2 * j + 1] = pack_hi(a1, b1); w2[2 * j + 1] = pack_hi(a2, b2); w3[2 * j + 1] = pack_hi(a3, b3);
+          // r = (R_big + R_small) - x, two roundings
+          const float2 ra = sub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 0]), __uint_as_float(rb[4 * j + 1])),
+                                            make_float2(__uint_as_float(rs[4 * j + 0]), __uint_as_float(rs[4 * j + 1]))),
+                                 make_float2(xv[j].x, xv[j].y));
+          const float2 rc = sub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3])),
+                                            make_float2(__uint_as_float(rs[4 * j + 2]), __uint_as_float(rs[4 * j + 3]))),
+                                 make_float2(xv[j].z, xv[j].w));
+          split3_pair(ra, w1[2 * j], w2[2 * j], w3[2 * j]);
+          split3_pair(rc, w1[2 * j + 1], w2[2 * j + 1], w3[2 * j + 1]);
         }
         const uint32_t t_r = tbase + lane_base + kColStage + grp * 16;
         tmem_st16(t_r, w1);
@@ -346,12 +447,22 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bar_rready);
+        TRACE(31);
       }
       // ---------------- phase C: fused update ----------------
+      // z_next goes to HBM as coalesced TMA stores: the group stages each 64-atom chunk
+      // (two [128 x 32] boxes, 128-byte swizzle, conflict-free 16-byte writes) in the input
+      // stage it consumed last in phase A and withheld from the producer (keep_stage).
+      uint8_t* out_s = smem + kSmemStage + keep_stage * kStageBytes;
+      const bool store_leader = (warp == 2 + 4 * grp) && (lane == 0);
       for (int q = grp; q < nq; q += 2) {
         TC_WAIT(&bar_gfull[grp], g_cnt & 1);
+        TRACE(40);
         ++g_cnt;
         tc_fence_after();
+        // the previous chunk's TMA stores must have finished READING the staging buffer
+        if (store_leader) tma_store_wait_read<0>();
+        group_sync(grp);
         const uint32_t t_g = tbase + lane_base + (grp ? kColAcc1 : kColAcc0);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -359,28 +470,45 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
           tmem_ld32(t_g + h * 32, g);
           tmem_ld32(tbase + lane_base + kColY + q * kQ + h * 32, yv);
           tmem_wait_ld();
-          const int col0 = q * kQ + h * 32;
-          if (grow < p.n) {
-            float* dst = p.z_io + grow * p.k + col0;
+          if (h == 1) {
+            // accumulator fully read: hand the G buffer back before the stores
+            tc_fence_before();
+            mbar_arrive(&bar_gfree[grp]);
+          }
+          uint8_t* box = out_s + h * kBoxBytes;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (col0 + 4 * j < p.k) {
-                float4 o;
-                o.x = ista_update(__uint_as_float(yv[4 * j + 0]), __uint_as_float(g[4 * j + 0]), p.lr, p.lam);
-                o.y = ista_update(__uint_as_float(yv[4 * j + 1]), __uint_as_float(g[4 * j + 1]), p.lr, p.lam);
-                o.z = ista_update(__uint_as_float(yv[4 * j + 2]), __uint_as_float(g[4 * j + 2]), p.lr, p.lam);
-                o.w = ista_update(__uint_as_float(yv[4 * j + 3]), __uint_as_float(g[4 * j + 3]), p.lr, p.lam);
-                *reinterpret_cast<float4*>(dst + 4 * j) = o;
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float2 oa = ista_update_pair(
+                make_float2(__uint_as_float(yv[4 * j + 0]), __uint_as_float(yv[4 * j + 1])),
+                make_float2(__uint_as_float(g[4 * j + 0]), __uint_as_float(g[4 * j + 1])), lr2, p.lam);
+            const float2 oc = ista_update_pair(
+                make_float2(__uint_as_float(yv[4 * j + 2]), __uint_as_float(yv[4 * j + 3])),
+                make_float2(__uint_as_float(g[4 * j + 2]), __uint_as_float(g[4 * j + 3])), lr2, p.lam);
+            *reinterpret_cast<float4*>(box + sw128_offset(row, j * 16)) =
+                make_float4(oa.x, oa.y, oc.x, oc.y);
           }
         }
-        tc_fence_before();
-        mbar_arrive(&bar_gfree[grp]);
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
+        group_sync(grp);
+        if (store_leader) {
+          const int row0 = (int)(tile * kTileM);
+          tma_store_2d(tm_prev, out_s, q * kQ, row0);               // rows / columns beyond
+          tma_store_2d(tm_prev, out_s + kBoxBytes, q * kQ + 32, row0);  // n, k are clipped
+          tma_store_commit();
+        }
+        TRACE(41);
+      }
+      if (has_out) {
+        // release the withheld stage to the producer once the last stores have read it
+        if (store_leader) tma_store_wait_read<0>();
+        group_sync(grp);
+        mbar_arrive(&bar_empty[keep_stage]);
       }
       // y master / r pieces are rewritten by the next tile: all compute warps must be done
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      TRACE(50);
     }
+    if (warp == 2 || warp == 6) tma_store_wait_all<0>();
     // lagged stop-test sum of the previous iteration
     dsum = warp_sum(dsum);
     if (lane == 0) red[warp - 2] = dsum;
@@ -459,6 +587,7 @@ struct TcState {
   bool attr_set = false;
   int* dbg_host = nullptr;   // LASSO_B200_DEBUG=1: mapped record of the first barrier timeout
   int* dbg_dev = nullptr;
+  unsigned long long* trace = nullptr;   // LASSO_B200_TRACE=<file>
 };
 TcState g_tc[64];
 
@@ -482,6 +611,9 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     memset(S.dbg_host, 0, 65536);
     LASSO_CUDA_TRY(cudaHostGetDevicePointer((void**)&S.dbg_dev, S.dbg_host, 0));
   }
+  const char* trace_path = getenv("LASSO_B200_TRACE");
+  if (trace_path && !S.trace) LASSO_CUDA_TRY(cudaMalloc(&S.trace, 10 * 512 * 8));
+  if (S.trace) LASSO_CUDA_TRY(cudaMemsetAsync(S.trace, 0, 10 * 512 * 8, st));
   if (!S.attr_set) {
     LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kSmemBytes));
@@ -524,25 +656,25 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     p.ctl.tol_abs = a.tol_abs;
     p.ctl.iter = it;
     p.dbg = S.dbg_dev;
+    p.trace = (it == a.maxiter - 1) ? S.trace : nullptr;
     fista_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, p);
     LASSO_CHECK_LAUNCH();
     count_launch();
   }
+  if (S.trace && trace_path) {
+    static unsigned long long host_trace[10 * 512];
+    LASSO_CUDA_TRY(cudaMemcpyAsync(host_trace, S.trace, sizeof(host_trace), cudaMemcpyDeviceToHost, st));
+    LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int w = 0; w < 10; ++w)
+        for (int i = 0; i < 512 && host_trace[w * 512 + i]; ++i)
+          fprintf(f, "%d %llu %llu\n", w, host_trace[w * 512 + i] >> 8, host_trace[w * 512 + i] & 255);
+      fclose(f);
+    }
+  }
   if (S.dbg_host) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (S.dbg_host[0]) {
-      for (int b = 0; b < 148; ++b) {
-        bool any = false;
-        for (int wi = 0; wi < 10; ++wi) any |= S.dbg_host[64 + b * 16 + wi] != 0;
-        if (!any) continue;
-        fprintf(stderr, "[lasso_b200 dbg] block %3d:", b);
-        for (int wi = 0; wi < 10; ++wi) {
-          const int v = S.dbg_host[64 + b * 16 + wi];
-          const int a = v < 0 ? -v : v;
-          fprintf(stderr, " w%d=%s%d/%d", wi, v < 0 ? "T" : "", a / 16, a % 16);
-        }
-        fprintf(stderr, "\n");
-      }
       set_error("tcgen05 kernel barrier timeout: line %d block %d thread %d iter %d parity %d (%s)",
                 S.dbg_host[1], S.dbg_host[2], S.dbg_host[3], S.dbg_host[4], S.dbg_host[5],
                 cudaGetErrorString(e));

@@ -1,0 +1,27 @@
+"""Run one C2-sized solve with LASSO_B200_TRACE and print block 0's per-warp timeline."""
+import os, sys, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+path = os.environ.setdefault("LASSO_B200_TRACE", "/tmp/tc_trace.txt")
+import torch
+import lasso_b200, oracle
+from lasso_b200 import _cabi
+from lasso_b200.testing import make_problem
+n, d, k = 65536, 64, 256
+x, w = make_problem(n, d, k, seed=0)
+lr = 1.0 / oracle.lipschitz_constant(w)
+dev = torch.device("cuda", 0)
+_cabi.fista_device(x.to(dev), w.to(dev), None, 0.1, lr, 6, True, 0.0, path="tcgen05")
+torch.cuda.synchronize()
+ev = collections.defaultdict(list)
+for line in open(path):
+    wi, t, e = line.split(); ev[int(wi)].append((int(t), int(e)))
+t0 = min(t for v in ev.values() for t, _ in v)
+names = {1: "P:empty_ok", 10: "M:tile", 11: "M:aready_ok", 12: "M:commit_chunk", 13: "M:commit_rfull", 14: "M:rready_ok",
+         15: "M:gfree_ok", 16: "M:commit_g", 20: "C:full_ok", 21: "C:math_done", 22: "C:sfree_ok", 23: "C:st_done",
+         30: "C:rfull_ok", 31: "C:phaseB_done", 40: "C:gfull_ok", 41: "C:epi_done", 50: "C:tile_end"}
+for wi in (0, 1, 2, 6):
+    print("---- warp", wi)
+    prev = None
+    for t, e in ev[wi][:int(os.environ.get("TRACE_ROWS", "70"))]:
+        print("%8d  +%6d  %s" % (t - t0, (t - prev) if prev else 0, names.get(e, e)))
+        prev = t
