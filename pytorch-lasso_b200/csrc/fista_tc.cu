@@ -63,6 +63,7 @@ struct TcParams {
   float* z_io;             // z_prev on entry, z_next on exit
   int64_t n;
   int d, k;
+  int tile_rows;           // rows per tile (<= 128): chosen so that the last wave of tiles is full
   float lr, lam, beta;
   int use_prev;
   int cur_is_a;            // which tensor map holds z_cur
@@ -175,7 +176,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int tr_n = 0;
-  const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
+  const int64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
   const int nc = (p.k + kChunk - 1) / kChunk;   // phase-A chunks
   const int nq = (p.k + kQ - 1) / kQ;           // GEMM2 chunks
   const int dsteps = (p.d + 15) / 16;           // k-steps of GEMM2
@@ -222,7 +223,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     // phase of the barrier, which is all a parity wait can disambiguate.
     uint32_t m0 = 0, m1 = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int row0 = (int)(tile * kTileM);
+      const int row0 = (int)(tile * p.tile_rows);
       for (int c = 0; c < nc; ++c) {
         const int g = c & 1;
         const uint32_t mg = g ? m1 : m0;
@@ -231,7 +232,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         TC_WAIT(&bar_empty[s], ph ^ 1);
         TRACE(1);
         if (elect_one()) {
-          mbar_expect_tx(&bar_full[s], kStageBytes);
+          mbar_expect_tx(&bar_full[s], 2u * (uint32_t)p.tile_rows * 128u);
           uint8_t* dst = smem + kSmemStage + s * kStageBytes;
           tma_load_2d(dst, tm_cur, c * kChunk, row0, &bar_full[s]);
           tma_load_2d(dst + kBoxBytes, tm_prev, c * kChunk, row0, &bar_full[s]);
@@ -294,8 +295,11 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
             // leading product -> R_big
             mma_ts<false>(tbase + kColAcc0, p1, q1, idesc1, acc_on);
           }
-          mma_commit(&bar_sfree[b]);
+          // one commit per chunk: the tile's last chunk signals "GEMM1 complete" instead of
+          // "piece stage free" (two back-to-back commits stall the issuing thread until the
+          // first one retires)
           if (c == nc - 1) mma_commit(&bar_rfull);
+          else mma_commit(&bar_sfree[b]);
         }
         __syncwarp();
         TRACE(12);
@@ -347,12 +351,14 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     double dsum = 0.0;
     const float2 lr2 = make_float2(p.lr, p.lr);
     const bool has_out = nq > grp;   // this group owns at least one GEMM2 chunk per tile
-    uint32_t a_cnt = 0, g_cnt = 0, ti = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-      const int64_t grow = tile * kTileM + row;
+    uint32_t a_cnt = 0, g_cnt = 0, ti = 0, sf_base = 0;
+    const uint32_t sf_per_tile = (uint32_t)((nc - grp + 1) / 2) - ((((nc - 1) & 1) == grp) ? 1u : 0u);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti, sf_base += sf_per_tile) {
+      const int64_t grow = tile * p.tile_rows + row;
+      const bool row_ok = row < p.tile_rows && grow < p.n;   // lanes beyond the tile carry stale data
       uint32_t keep_stage = grp;   // set in phase A whenever has_out
       // pull this thread's 128-byte slice of x towards L2 now; phase B reads it ~10k cycles later
-      if (grow < p.n && grp * 32 < p.d)
+      if (row_ok && grp * 32 < p.d)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + grow * p.d + grp * 32));
       // ---------------- phase A ----------------
       for (int c = grp; c < nc; c += 2) {
@@ -391,10 +397,13 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         // phase C stages its output there and releases it afterwards.
         if (has_out && c + 2 >= nc) keep_stage = s;
         else mbar_arrive(&bar_empty[s]);
-        dsum += (double)part;
+        if (row_ok) dsum += (double)part;
         // the piece stage is free once the MMAs of its previous chunk completed
         TRACE(21);
-        TC_WAIT(&bar_sfree[grp], (a_cnt & 1) ^ 1);
+        // (its first chunk of a tile needs no wait: everybody saw GEMM1 of the previous tile
+        // complete).  Phases of bar_sfree are counted in sf_base: one per chunk of this group
+        // except the tile's very last chunk, which commits to bar_rfull instead.
+        if (c >= 2) TC_WAIT(&bar_sfree[grp], (sf_base + (uint32_t)(c >> 1) - 1u) & 1u);
         TRACE(22);
         ++a_cnt;
         tc_fence_after();
@@ -417,7 +426,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         for (int j = 0; j < 8; ++j) {
           const int col = grp * 32 + 4 * j;
           xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (grow < p.n && col < p.d)
+          if (row_ok && col < p.d)
             xv[j] = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.d + col));
         }
         TC_WAIT(&bar_rfull, ti & 1);
@@ -491,7 +500,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
         group_sync(grp);
         if (store_leader) {
-          const int row0 = (int)(tile * kTileM);
+          const int row0 = (int)(tile * p.tile_rows);
           tma_store_2d(tm_prev, out_s, q * kQ, row0);               // rows / columns beyond
           tma_store_2d(tm_prev, out_s + kBoxBytes, q * kQ + 32, row0);  // n, k are clipped
           tma_store_commit();
@@ -560,7 +569,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows][cols] row-major, box = [128 rows][32 cols], 128-byte swizzle
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int tile_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -568,7 +577,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int cols) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)kTileM};
+  cuuint32_t box[2] = {32, (cuuint32_t)tile_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -623,13 +632,20 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   LASSO_CHECK_LAUNCH();
   count_launch();
 
+  // Tile height: the smallest multiple of 8 rows for which the tiles still fit the same number
+  // of waves as 128-row tiles would need -- the last wave is then (almost) full instead of
+  // leaving SMs idle (n = 65536 on 148 SMs: 592 slots, 111 -> 112 rows, 586 tiles).
+  const int64_t waves = ((a.n + kTileM - 1) / kTileM + S.num_sms - 1) / S.num_sms;
+  int64_t tile_rows = (a.n + waves * S.num_sms - 1) / (waves * S.num_sms);
+  tile_rows = ((tile_rows + 7) / 8) * 8;
+  if (tile_rows > kTileM) tile_rows = kTileM;
+  const int64_t ntiles = (a.n + tile_rows - 1) / tile_rows;
+  const unsigned grid = (unsigned)(ntiles < S.num_sms ? ntiles : S.num_sms);
   CUtensorMap tm_za, tm_zb;
   int rc;
-  if ((rc = make_map(&tm_za, a.z_a, a.n, a.k))) return rc;
-  if ((rc = make_map(&tm_zb, a.z_b, a.n, a.k))) return rc;
+  if ((rc = make_map(&tm_za, a.z_a, a.n, a.k, (int)tile_rows))) return rc;
+  if ((rc = make_map(&tm_zb, a.z_b, a.n, a.k, (int)tile_rows))) return rc;
 
-  const int64_t ntiles = (a.n + kTileM - 1) / kTileM;
-  const unsigned grid = (unsigned)(ntiles < S.num_sms ? ntiles : S.num_sms);
   double t = 1.0;
   for (int it = 0; it < a.maxiter; ++it) {
     TcParams p{};
@@ -640,6 +656,7 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     p.n = a.n;
     p.d = a.d;
     p.k = a.k;
+    p.tile_rows = (int)tile_rows;
     p.lr = a.lr;
     p.lam = a.lam;
     double beta = 0.0;
