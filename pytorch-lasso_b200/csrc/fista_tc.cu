@@ -39,7 +39,7 @@ constexpr int kQ = 64;           // atoms per GEMM2 chunk (one 128-byte bf16 row
 constexpr int kDP = 64;          // padded d
 constexpr int kKP = 256;         // padded k
 constexpr int kStages = 4;       // two per compute group (fixed ownership, see phase A)
-constexpr int kThreads = 320;    // warp 0: TMA, warp 1: MMA, warps 2..9: compute
+constexpr int kThreads = 576;    // warp 0: TMA, warp 1: MMA, warps 2..17: compute (4 groups)
 
 constexpr uint32_t kSlabBytes = kDP * 128;               // [64 rows][128 B] = 64 atoms of one piece
 constexpr uint32_t kPieceBytes = (kKP / 64) * kSlabBytes;  // 32 KB
@@ -130,9 +130,10 @@ __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) {
   return __byte_perm(a, b, 0x7632);
 }
 
-// named barrier of one compute group (4 warps); ids 2 and 3 (0 = __syncthreads, 1 = all compute)
-__device__ __forceinline__ void group_sync(int grp) {
-  asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+// named barrier of one pair of compute groups (8 warps); ids 2 and 3
+// (0 = __syncthreads, 1 = all compute warps)
+__device__ __forceinline__ void pair_sync(int grp) {
+  asm volatile("bar.sync %0, 256;" ::"r"(2 + grp) : "memory");
 }
 
 // ---- packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot per pair.
@@ -168,7 +169,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   __shared__ uint64_t bar_w, bar_full[kStages], bar_empty[kStages];
   __shared__ uint64_t bar_aready[2], bar_sfree[2], bar_rfull, bar_rready, bar_gfull[2], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ double red[8];
+  __shared__ double red[16];
 
   // stop test of two iterations ago already satisfied -> this launch is a no-op.
   // (hist[iter-1] is produced by THIS launch, see phase A.)
@@ -187,16 +188,16 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     mbar_init(&bar_w, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 128);
+      mbar_init(&bar_empty[s], 256);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_aready[b], 128);
+      mbar_init(&bar_aready[b], 256);
       mbar_init(&bar_sfree[b], 1);
       mbar_init(&bar_gfull[b], 1);
-      mbar_init(&bar_gfree[b], 128);
+      mbar_init(&bar_gfree[b], 256);
     }
     mbar_init(&bar_rfull, 1);
-    mbar_init(&bar_rready, 256);
+    mbar_init(&bar_rready, 512);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -344,38 +345,44 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     }
   } else {
     // ===================== compute warps =====================
+    // 16 warps = 4 groups of 4 (a group covers the 128 TMEM lanes).  Groups {0,2} own the
+    // even phase-A chunks / G buffer 0, groups {1,3} the odd ones / G buffer 1 ("pair" = wg & 1);
+    // inside a pair the two groups split the columns of every chunk in halves (wg >> 1).
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int grp = (warp - 2) >> 2;           // 0 / 1: which chunks / G buffer
+    const int wg = (warp - 2) >> 2;            // 0..3
+    const int grp = wg & 1;                    // pair: stage ring / piece stage / G buffer
+    const int half = wg >> 1;                  // which half of the pair's columns
     const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     double dsum = 0.0;
     const float2 lr2 = make_float2(p.lr, p.lr);
-    const bool has_out = nq > grp;   // this group owns at least one GEMM2 chunk per tile
+    const float2 beta2 = make_float2(p.beta, p.beta);
+    const bool has_out = nq > grp;   // this pair owns at least one GEMM2 chunk per tile
+    const bool store_leader = (wg == grp) && (quad == 2) && (lane == 0);   // warp 2 / warp 6
     uint32_t a_cnt = 0, g_cnt = 0, ti = 0, sf_base = 0;
     const uint32_t sf_per_tile = (uint32_t)((nc - grp + 1) / 2) - ((((nc - 1) & 1) == grp) ? 1u : 0u);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti, sf_base += sf_per_tile) {
       const int64_t grow = tile * p.tile_rows + row;
       const bool row_ok = row < p.tile_rows && grow < p.n;   // lanes beyond the tile carry stale data
       uint32_t keep_stage = grp;   // set in phase A whenever has_out
-      // pull this thread's 128-byte slice of x towards L2 now; phase B reads it ~10k cycles later
-      if (row_ok && grp * 32 < p.d)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + grow * p.d + grp * 32));
+      // pull this thread's 64-byte slice of x towards L2 now; phase B reads it ~10k cycles later
+      if (row_ok && wg * 16 < p.d)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + grow * p.d + wg * 16));
       // ---------------- phase A ----------------
       for (int c = grp; c < nc; c += 2) {
-        // a_cnt = chunks this group consumed so far = index into its private stage ring
+        // a_cnt = chunks this pair consumed so far = index into its private stage ring
         const uint32_t s = grp + 2 * (a_cnt & 1), ph = (a_cnt >> 1) & 1;
         TC_WAIT(&bar_full[s], ph);
         TRACE(20);
         const uint8_t* zc_s = smem + kSmemStage + s * kStageBytes;
         const uint8_t* zp_s = zc_s + kBoxBytes;
         // y = z_cur + beta (z_cur - z_prev) on fp32 pairs; |z_cur - z_prev| feeds the lagged
-        // stop-test sum; then the exact three-way bf16 split of every y
-        uint32_t yb[kChunk], w1[16], w2[16], w3[16];
+        // stop-test sum; then the exact three-way bf16 split of every y (16 atoms per thread)
+        uint32_t yb[16], w1[8], w2[8], w3[8];
         float part = 0.f;
-        const float2 beta2 = make_float2(p.beta, p.beta);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t off = sw128_offset(row, j * 16);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = sw128_offset(row, (half * 4 + j) * 16);
           const float4 zc = *reinterpret_cast<const float4*>(zc_s + off);
           float2 ya = make_float2(zc.x, zc.y), yc = make_float2(zc.z, zc.w);
           if (p.use_prev) {
@@ -398,33 +405,33 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         if (has_out && c + 2 >= nc) keep_stage = s;
         else mbar_arrive(&bar_empty[s]);
         if (row_ok) dsum += (double)part;
-        // the piece stage is free once the MMAs of its previous chunk completed
         TRACE(21);
-        // (its first chunk of a tile needs no wait: everybody saw GEMM1 of the previous tile
-        // complete).  Phases of bar_sfree are counted in sf_base: one per chunk of this group
-        // except the tile's very last chunk, which commits to bar_rfull instead.
+        // The piece stage is free once the MMAs of its previous chunk completed (the first
+        // chunk of a tile needs no wait: everybody saw GEMM1 of the previous tile complete).
+        // Phases of bar_sfree are counted in sf_base: one per chunk of this pair except the
+        // tile's very last chunk, which commits to bar_rfull instead.
         if (c >= 2) TC_WAIT(&bar_sfree[grp], (sf_base + (uint32_t)(c >> 1) - 1u) & 1u);
         TRACE(22);
         ++a_cnt;
         tc_fence_after();
-        tmem_st32(tbase + lane_base + kColY + c * kChunk, yb);
-        const uint32_t t_stage = tbase + lane_base + kColStage + grp * 48;
-        tmem_st16(t_stage, w1);
-        tmem_st16(t_stage + 16, w2);
-        tmem_st16(t_stage + 32, w3);
+        tmem_st16(tbase + lane_base + kColY + c * kChunk + half * 16, yb);
+        const uint32_t t_stage = tbase + lane_base + kColStage + grp * 48 + half * 8;
+        tmem_st8(t_stage, w1);
+        tmem_st8(t_stage + 16, w2);
+        tmem_st8(t_stage + 32, w3);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bar_aready[grp]);
         TRACE(23);
       }
-      // ---------------- phase B: r = R - x, pieces of r ----------------
+      // ---------------- phase B: r = R - x, pieces of r (16 features per thread) ----------------
       {
-        // this thread's 32 features of x, straight from global (issued before the wait on
-        // GEMM1 so the latency overlaps the tail of the MMAs)
-        float4 xv[8];
+        // this thread's features of x, straight from global (prefetched into L2 at tile start;
+        // issued before the wait on GEMM1 so the latency overlaps the tail of the MMAs)
+        float4 xv[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = grp * 32 + 4 * j;
+        for (int j = 0; j < 4; ++j) {
+          const int col = wg * 16 + 4 * j;
           xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row_ok && col < p.d)
             xv[j] = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.d + col));
@@ -432,13 +439,13 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         TC_WAIT(&bar_rfull, ti & 1);
         TRACE(30);
         tc_fence_after();
-        uint32_t rb[32], rs[32];
-        tmem_ld32(tbase + lane_base + kColAcc0 + grp * 32, rb);
-        tmem_ld32(tbase + lane_base + kColAcc1 + grp * 32, rs);
+        uint32_t rb[16], rs[16];
+        tmem_ld16(tbase + lane_base + kColAcc0 + wg * 16, rb);
+        tmem_ld16(tbase + lane_base + kColAcc1 + wg * 16, rs);
         tmem_wait_ld();
-        uint32_t w1[16], w2[16], w3[16];
+        uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           // r = (R_big + R_small) - x, two roundings
           const float2 ra = sub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 0]), __uint_as_float(rb[4 * j + 1])),
                                             make_float2(__uint_as_float(rs[4 * j + 0]), __uint_as_float(rs[4 * j + 1]))),
@@ -449,56 +456,49 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
           split3_pair(ra, w1[2 * j], w2[2 * j], w3[2 * j]);
           split3_pair(rc, w1[2 * j + 1], w2[2 * j + 1], w3[2 * j + 1]);
         }
-        const uint32_t t_r = tbase + lane_base + kColStage + grp * 16;
-        tmem_st16(t_r, w1);
-        tmem_st16(t_r + 32, w2);
-        tmem_st16(t_r + 64, w3);
+        const uint32_t t_r = tbase + lane_base + kColStage + wg * 8;
+        tmem_st8(t_r, w1);
+        tmem_st8(t_r + 32, w2);
+        tmem_st8(t_r + 64, w3);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bar_rready);
         TRACE(31);
       }
       // ---------------- phase C: fused update ----------------
-      // z_next goes to HBM as coalesced TMA stores: the group stages each 64-atom chunk
-      // (two [128 x 32] boxes, 128-byte swizzle, conflict-free 16-byte writes) in the input
-      // stage it consumed last in phase A and withheld from the producer (keep_stage).
+      // z_next goes to HBM as coalesced TMA stores: the pair stages each 64-atom chunk (two
+      // [128 x 32] boxes, one per group, 128-byte swizzle, conflict-free 16-byte writes) in
+      // the input stage it consumed last in phase A and withheld from the producer.
       uint8_t* out_s = smem + kSmemStage + keep_stage * kStageBytes;
-      const bool store_leader = (warp == 2 + 4 * grp) && (lane == 0);
       for (int q = grp; q < nq; q += 2) {
         TC_WAIT(&bar_gfull[grp], g_cnt & 1);
         TRACE(40);
         ++g_cnt;
         tc_fence_after();
+        uint32_t g[32], yv[32];
+        tmem_ld32(tbase + lane_base + (grp ? kColAcc1 : kColAcc0) + half * 32, g);
+        tmem_ld32(tbase + lane_base + kColY + q * kQ + half * 32, yv);
         // the previous chunk's TMA stores must have finished READING the staging buffer
         if (store_leader) tma_store_wait_read<0>();
-        group_sync(grp);
-        const uint32_t t_g = tbase + lane_base + (grp ? kColAcc1 : kColAcc0);
+        pair_sync(grp);
+        tmem_wait_ld();
+        // accumulator read: hand the G buffer back before the stores
+        tc_fence_before();
+        mbar_arrive(&bar_gfree[grp]);
+        uint8_t* box = out_s + half * kBoxBytes;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t g[32], yv[32];
-          tmem_ld32(t_g + h * 32, g);
-          tmem_ld32(tbase + lane_base + kColY + q * kQ + h * 32, yv);
-          tmem_wait_ld();
-          if (h == 1) {
-            // accumulator fully read: hand the G buffer back before the stores
-            tc_fence_before();
-            mbar_arrive(&bar_gfree[grp]);
-          }
-          uint8_t* box = out_s + h * kBoxBytes;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 oa = ista_update_pair(
-                make_float2(__uint_as_float(yv[4 * j + 0]), __uint_as_float(yv[4 * j + 1])),
-                make_float2(__uint_as_float(g[4 * j + 0]), __uint_as_float(g[4 * j + 1])), lr2, p.lam);
-            const float2 oc = ista_update_pair(
-                make_float2(__uint_as_float(yv[4 * j + 2]), __uint_as_float(yv[4 * j + 3])),
-                make_float2(__uint_as_float(g[4 * j + 2]), __uint_as_float(g[4 * j + 3])), lr2, p.lam);
-            *reinterpret_cast<float4*>(box + sw128_offset(row, j * 16)) =
-                make_float4(oa.x, oa.y, oc.x, oc.y);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float2 oa = ista_update_pair(
+              make_float2(__uint_as_float(yv[4 * j + 0]), __uint_as_float(yv[4 * j + 1])),
+              make_float2(__uint_as_float(g[4 * j + 0]), __uint_as_float(g[4 * j + 1])), lr2, p.lam);
+          const float2 oc = ista_update_pair(
+              make_float2(__uint_as_float(yv[4 * j + 2]), __uint_as_float(yv[4 * j + 3])),
+              make_float2(__uint_as_float(g[4 * j + 2]), __uint_as_float(g[4 * j + 3])), lr2, p.lam);
+          *reinterpret_cast<float4*>(box + sw128_offset(row, j * 16)) =
+              make_float4(oa.x, oa.y, oc.x, oc.y);
         }
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
-        group_sync(grp);
+        pair_sync(grp);
         if (store_leader) {
           const int row0 = (int)(tile * p.tile_rows);
           tma_store_2d(tm_prev, out_s, q * kQ, row0);               // rows / columns beyond
@@ -510,21 +510,21 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
       if (has_out) {
         // release the withheld stage to the producer once the last stores have read it
         if (store_leader) tma_store_wait_read<0>();
-        group_sync(grp);
+        pair_sync(grp);
         mbar_arrive(&bar_empty[keep_stage]);
       }
       // y master / r pieces are rewritten by the next tile: all compute warps must be done
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       TRACE(50);
     }
-    if (warp == 2 || warp == 6) tma_store_wait_all<0>();
+    if (store_leader) tma_store_wait_all<0>();
     // lagged stop-test sum of the previous iteration
     dsum = warp_sum(dsum);
     if (lane == 0) red[warp - 2] = dsum;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     if (warp == 2 && lane == 0 && p.use_prev && p.ctl.hist != nullptr && p.ctl.iter >= 1) {
       double s = 0.0;
-      for (int i = 0; i < 8; ++i) s += red[i];
+      for (int i = 0; i < 16; ++i) s += red[i];
       atomicAdd(&p.ctl.hist[p.ctl.iter - 1], s);
     }
   }
