@@ -59,8 +59,8 @@ def problem():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons; only samples inside [t_begin, t_end] are kept."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -74,12 +74,17 @@ class ClockSampler:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+            return
+        # nvidia-smi needs a moment to initialise NVML: wait for its first line
+        deadline = time.time() + 10.0
+        while time.time() < deadline and os.path.getsize(self.file.name) == 0:
+            time.sleep(0.05)
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -87,29 +92,32 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        import datetime
         self.file.flush()
         self.file.seek(0)
-        sm, mx, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.file.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                power.append(float(parts[3]))
+                stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((stamp, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         self.file.close()
         os.unlink(self.file.name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t_begin <= r[0] <= t_end]
+        window = "timed region"
+        if not inside:   # region shorter than the sampling period: nearest samples around it
+            inside = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t_begin + t_end)))[:3]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in inside for n, v in zip(names, r[4]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(r[1] for r in inside) if inside else None,
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "power_w_max": max(r[3] for r in inside) if inside else None,
+                "samples": len(inside), "window": window, "reasons": reasons}
 
 
 def cpu_reference_rate(x, w, lr, budget_s=12.0, threads=None):
@@ -219,10 +227,13 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+        device_step()          # keep the GPU busy while the sampler settles
     launches0 = _cabi.launch_count()
+    t_begin = time.time()
     ms = timed(device_step, args.steps)
+    t_end = time.time()
     launches = _cabi.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     for _ in range(2):
         e2e_step()
@@ -286,7 +297,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tcgen05"])

@@ -73,22 +73,24 @@ int current_workspace(Workspace** out) {
   return LASSO_B200_OK;
 }
 
-// first iteration whose delta met the stop test, else maxiter-1; result index
-// written to ctl[0] = number of executed iterations.
+// ctl[0] = number of iterations the reference loop would have executed: index of the first
+// iteration (before the last) whose delta met the stop test, plus one; else maxiter.
 __global__ void find_stop_kernel(const double* __restrict__ hist, int maxiter, double tol_abs,
-                                 int lag_extra, int* __restrict__ ctl) {
-  // single thread: maxiter is small (tens to thousands)
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int done = maxiter;
+                                 int* __restrict__ ctl) {
+  __shared__ int best;
+  if (threadIdx.x == 0) best = maxiter;
+  __syncthreads();
   if (tol_abs >= 0.0) {
-    for (int i = 0; i < maxiter - 1; ++i)
+    int mine = maxiter;
+    for (int i = threadIdx.x; i < maxiter - 1; i += blockDim.x)
       if (hist[i] <= tol_abs) {
-        done = i + 1;
+        mine = i + 1;
         break;
       }
+    if (mine < maxiter) atomicMin(&best, mine);
   }
-  ctl[0] = done;
-  (void)lag_extra;
+  __syncthreads();
+  if (threadIdx.x == 0) ctl[0] = best;
 }
 
 // copy the buffer that holds z_done into z_out when it is not already there
@@ -208,7 +210,7 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
 
   int* ctl = (int*)ws->ctl.ptr;
   if (tol_abs >= 0.0 || iters_done) {
-    find_stop_kernel<<<1, 32, 0, st>>>(hist, maxiter, tol_abs, 0, ctl);
+    find_stop_kernel<<<1, 256, 0, st>>>(hist, maxiter, tol_abs, ctl);
     LASSO_CHECK_LAUNCH();
     count_launch();
   }
