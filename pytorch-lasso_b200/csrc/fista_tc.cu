@@ -533,6 +533,8 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   if (warp == 1) tmem_dealloc(tbase, kTmemCols);
 }
 
+#include "fista_tc2.cuh"
+
 // dictionary [d][k] fp32 -> three bf16 piece images, each [k/64 slabs][64 rows][128 B] with
 // the 128-byte swizzle; zero padded to d = 64, k = 256.
 __global__ void prep_w_image_kernel(const float* __restrict__ w, int d, int k,
@@ -621,10 +623,12 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     LASSO_CUDA_TRY(cudaHostGetDevicePointer((void**)&S.dbg_dev, S.dbg_host, 0));
   }
   const char* trace_path = getenv("LASSO_B200_TRACE");
-  if (trace_path && !S.trace) LASSO_CUDA_TRY(cudaMalloc(&S.trace, 10 * 512 * 8));
-  if (S.trace) LASSO_CUDA_TRY(cudaMemsetAsync(S.trace, 0, 10 * 512 * 8, st));
+  if (trace_path && !S.trace) LASSO_CUDA_TRY(cudaMalloc(&S.trace, 32 * 512 * 8));
+  if (S.trace) LASSO_CUDA_TRY(cudaMemsetAsync(S.trace, 0, 32 * 512 * 8, st));
   if (!S.attr_set) {
     LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kSmemBytes));
+    LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kSmemBytes));
     S.attr_set = true;
   }
@@ -635,8 +639,12 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   // Tile height: the smallest multiple of 8 rows for which the tiles still fit the same number
   // of waves as 128-row tiles would need -- the last wave is then (almost) full instead of
   // leaving SMs idle (n = 65536 on 148 SMs: 592 slots, 111 -> 112 rows, 586 tiles).
-  const int64_t waves = ((a.n + kTileM - 1) / kTileM + S.num_sms - 1) / S.num_sms;
-  int64_t tile_rows = (a.n + waves * S.num_sms - 1) / (waves * S.num_sms);
+  // kernel version: 2 = two tiles in flight per SM (default), 1 = single tile with a y master
+  const char* ver_env = getenv("LASSO_B200_TC_VERSION");
+  const int version = (ver_env && ver_env[0] == '1') ? 1 : 2;
+  const int64_t slots = (int64_t)S.num_sms * version;
+  const int64_t waves = ((a.n + kTileM - 1) / kTileM + slots - 1) / slots;
+  int64_t tile_rows = (a.n + waves * slots - 1) / (waves * slots);
   tile_rows = ((tile_rows + 7) / 8) * 8;
   if (tile_rows > kTileM) tile_rows = kTileM;
   const int64_t ntiles = (a.n + tile_rows - 1) / tile_rows;
@@ -674,16 +682,17 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     p.ctl.iter = it;
     p.dbg = S.dbg_dev;
     p.trace = (it == a.maxiter - 1) ? S.trace : nullptr;
-    fista_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, p);
+    if (version == 1) fista_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, p);
+    else fista_tc2_kernel<<<grid, kThreads2, kSmemBytes, st>>>(tm_za, tm_zb, p);
     LASSO_CHECK_LAUNCH();
     count_launch();
   }
   if (S.trace && trace_path) {
-    static unsigned long long host_trace[10 * 512];
+    static unsigned long long host_trace[32 * 512];
     LASSO_CUDA_TRY(cudaMemcpyAsync(host_trace, S.trace, sizeof(host_trace), cudaMemcpyDeviceToHost, st));
     LASSO_CUDA_TRY(cudaStreamSynchronize(st));
     if (FILE* f = fopen(trace_path, "w")) {
-      for (int w = 0; w < 10; ++w)
+      for (int w = 0; w < 32; ++w)
         for (int i = 0; i < 512 && host_trace[w * 512 + i]; ++i)
           fprintf(f, "%d %llu %llu\n", w, host_trace[w * 512 + i] >> 8, host_trace[w * 512 + i] & 255);
       fclose(f);

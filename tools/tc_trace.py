@@ -19,7 +19,7 @@ t0 = min(t for v in ev.values() for t, _ in v)
 names = {1: "P:empty_ok", 10: "M:tile", 11: "M:aready_ok", 12: "M:commit_chunk", 13: "M:commit_rfull", 14: "M:rready_ok",
          15: "M:gfree_ok", 16: "M:commit_g", 20: "C:full_ok", 21: "C:math_done", 22: "C:sfree_ok", 23: "C:st_done",
          30: "C:rfull_ok", 31: "C:phaseB_done", 40: "C:gfull_ok", 41: "C:epi_done", 50: "C:tile_end"}
-for wi in (0, 1, 2, 6):
+for wi in [int(v) for v in os.environ.get("TRACE_WARPS", "0,2,4,12").split(",")]:
     print("---- warp", wi)
     prev = None
     for t, e in ev[wi][:int(os.environ.get("TRACE_ROWS", "70"))]:
