@@ -162,6 +162,7 @@ __device__ __forceinline__ float2 ista_update_pair(float2 y, float2 g, float2 lr
   return sub2(v, c);
 }
 
+template <int kDSteps>
 __global__ void __launch_bounds__(kThreads, 1)
 fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant__ CUtensorMap tm_zb,
                 TcParams p) {
@@ -180,7 +181,8 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   const int64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
   const int nc = (p.k + kChunk - 1) / kChunk;   // phase-A chunks
   const int nq = (p.k + kQ - 1) / kQ;           // GEMM2 chunks
-  const int dsteps = (p.d + 15) / 16;           // k-steps of GEMM2
+  constexpr int dsteps = kDSteps;               // k-steps of GEMM2 = ceil(d / 16), compile time so
+                                                // that every MMA descriptor is base + constant
   const CUtensorMap* tm_cur = p.cur_is_a ? &tm_za : &tm_zb;
   const CUtensorMap* tm_prev = p.cur_is_a ? &tm_zb : &tm_za;
 
@@ -330,6 +332,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
             constexpr int pa[6] = {2, 1, 0, 1, 0, 0}, pb[6] = {0, 1, 2, 0, 1, 0};
+#pragma unroll
             for (int ks = 0; ks < dsteps; ++ks) {
               // 16 k-rows of 128 B per k-step = 2048 B = 128 units
               const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
@@ -626,10 +629,12 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   if (trace_path && !S.trace) LASSO_CUDA_TRY(cudaMalloc(&S.trace, 32 * 512 * 8));
   if (S.trace) LASSO_CUDA_TRY(cudaMemsetAsync(S.trace, 0, 32 * 512 * 8, st));
   if (!S.attr_set) {
-    LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)kSmemBytes));
-    LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)kSmemBytes));
+    const void* kernels[8] = {(const void*)fista_tc_kernel<1>, (const void*)fista_tc_kernel<2>,
+                              (const void*)fista_tc_kernel<3>, (const void*)fista_tc_kernel<4>,
+                              (const void*)fista_tc2_kernel<1>, (const void*)fista_tc2_kernel<2>,
+                              (const void*)fista_tc2_kernel<3>, (const void*)fista_tc2_kernel<4>};
+    for (const void* kfn : kernels)
+      LASSO_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     S.attr_set = true;
   }
   prep_w_image_kernel<<<(kDP * kKP + 255) / 256, 256, 0, st>>>(a.w, a.d, a.k, S.w_image);
@@ -639,9 +644,10 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   // Tile height: the smallest multiple of 8 rows for which the tiles still fit the same number
   // of waves as 128-row tiles would need -- the last wave is then (almost) full instead of
   // leaving SMs idle (n = 65536 on 148 SMs: 592 slots, 111 -> 112 rows, 586 tiles).
-  // kernel version: 2 = two tiles in flight per SM (default), 1 = single tile with a y master
+  // kernel version: 1 = single tile per SM with a y master in TMEM (default, faster at <= 4 tiles per
+  // SM), 2 = two tiles in flight per SM (LASSO_B200_TC_VERSION=2)
   const char* ver_env = getenv("LASSO_B200_TC_VERSION");
-  const int version = (ver_env && ver_env[0] == '1') ? 1 : 2;
+  const int version = (ver_env && ver_env[0] == '2') ? 2 : 1;
   const int64_t slots = (int64_t)S.num_sms * version;
   const int64_t waves = ((a.n + kTileM - 1) / kTileM + slots - 1) / slots;
   int64_t tile_rows = (a.n + waves * slots - 1) / (waves * slots);
@@ -682,8 +688,19 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     p.ctl.iter = it;
     p.dbg = S.dbg_dev;
     p.trace = (it == a.maxiter - 1) ? S.trace : nullptr;
-    if (version == 1) fista_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, p);
-    else fista_tc2_kernel<<<grid, kThreads2, kSmemBytes, st>>>(tm_za, tm_zb, p);
+    const int dsteps = (a.d + 15) / 16;
+#define LASSO_TC_LAUNCH(DS)                                                                \
+  do {                                                                                     \
+    if (version == 1) fista_tc_kernel<DS><<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, p);   \
+    else fista_tc2_kernel<DS><<<grid, kThreads2, kSmemBytes, st>>>(tm_za, tm_zb, p);              \
+  } while (0)
+    switch (dsteps) {
+      case 1: LASSO_TC_LAUNCH(1); break;
+      case 2: LASSO_TC_LAUNCH(2); break;
+      case 3: LASSO_TC_LAUNCH(3); break;
+      default: LASSO_TC_LAUNCH(4); break;
+    }
+#undef LASSO_TC_LAUNCH
     LASSO_CHECK_LAUNCH();
     count_launch();
   }

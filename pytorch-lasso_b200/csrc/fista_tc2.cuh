@@ -24,6 +24,7 @@ struct SlotBarriers {
   uint64_t full[2], cons[2], aready[2], sfree[2], rfull, rready, gfull[2], gfree[2];
 };
 
+template <int kDSteps>
 __global__ void __launch_bounds__(kThreads2, 1)
 fista_tc2_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant__ CUtensorMap tm_zb,
                  TcParams p) {
@@ -40,7 +41,7 @@ fista_tc2_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constan
   const int64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
   const int nc = (p.k + kChunk - 1) / kChunk;   // 32-atom chunks (phase A) = sub-chunks (phase C)
   const int nq = (p.k + kQ - 1) / kQ;           // 64-atom GEMM2 chunks
-  const int dsteps = (p.d + 15) / 16;
+  constexpr int dsteps = kDSteps;   // ceil(d / 16)
   const CUtensorMap* tm_cur = p.cur_is_a ? &tm_za : &tm_zb;
   const CUtensorMap* tm_prev = p.cur_is_a ? &tm_zb : &tm_za;
 
@@ -210,6 +211,7 @@ fista_tc2_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constan
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
             constexpr int pa[6] = {2, 1, 0, 1, 0, 0}, pb[6] = {0, 1, 2, 0, 1, 0};
+#pragma unroll
             for (int ks = 0; ks < dsteps; ++ks) {
               const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
               mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
