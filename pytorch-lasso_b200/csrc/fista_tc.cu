@@ -67,6 +67,13 @@ struct TcParams {
   float lr, lam, beta;
   int use_prev;
   int cur_is_a;            // which tensor map holds z_cur
+  // v1 schedule: CTAs of class (blockIdx & 1) own contiguous row ranges cut into `waves` tiles of
+  // cls_rows[class] rows; class 1 starts stagger_cycles late and gets shorter tiles, so that half
+  // of the SMs stream codes (HBM-bound phase A) while the other half is in the MMA-bound phases.
+  int cls_rows[2];
+  int64_t cls_base[2], cls_end[2];
+  int waves;
+  int stagger_cycles;
   StepCtl ctl;
   volatile int* dbg;       // host-mapped debug record or nullptr
   unsigned long long* trace;  // LASSO_B200_TRACE: per-warp (clock << 8 | event) log of block 0
@@ -165,6 +172,7 @@ __device__ __forceinline__ float2 ista_update_pair(float2 y, float2 g, float2 lr
 template <int kDSteps>
 __global__ void __launch_bounds__(kThreads, 1)
 fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant__ CUtensorMap tm_zb,
+                const __grid_constant__ CUtensorMap tm_za1, const __grid_constant__ CUtensorMap tm_zb1,
                 TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_full[kStages], bar_empty[kStages];
@@ -178,13 +186,22 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int tr_n = 0;
-  const int64_t ntiles = (p.n + p.tile_rows - 1) / p.tile_rows;
+  // this CTA's rows: `my_tiles` tiles of `trows` rows starting at cta_row0 (see TcParams)
+  // (tiles of a class are interleaved over its CTAs: tile j of this CTA is class tile
+  //  (blockIdx >> 1) + j * cls_ctas; all row indices fit 32 bits, see fista_tc_supported)
+  const int cls = blockIdx.x & 1;
+  const int trows = p.cls_rows[cls];
+  const int cls_ctas = ((int)gridDim.x + 1 - cls) >> 1;
+  const int row_limit = (int)p.cls_end[cls];
+  const int first_row = (int)p.cls_base[cls] + (int)(blockIdx.x >> 1) * trows;
+  const int row_step = cls_ctas * trows;
+  const int my_tiles = first_row < row_limit ? (row_limit - first_row + row_step - 1) / row_step : 0;
   const int nc = (p.k + kChunk - 1) / kChunk;   // phase-A chunks
   const int nq = (p.k + kQ - 1) / kQ;           // GEMM2 chunks
   constexpr int dsteps = kDSteps;               // k-steps of GEMM2 = ceil(d / 16), compile time so
                                                 // that every MMA descriptor is base + constant
-  const CUtensorMap* tm_cur = p.cur_is_a ? &tm_za : &tm_zb;
-  const CUtensorMap* tm_prev = p.cur_is_a ? &tm_zb : &tm_za;
+  const CUtensorMap* tm_cur = cls ? (p.cur_is_a ? &tm_za1 : &tm_zb1) : (p.cur_is_a ? &tm_za : &tm_zb);
+  const CUtensorMap* tm_prev = cls ? (p.cur_is_a ? &tm_zb1 : &tm_za1) : (p.cur_is_a ? &tm_zb : &tm_za);
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
@@ -214,19 +231,23 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      prefetch_tmap(&tm_za);
-      prefetch_tmap(&tm_zb);
+      prefetch_tmap(tm_cur);
+      prefetch_tmap(tm_prev);
       mbar_expect_tx(&bar_w, kWBytes);
       for (uint32_t off = 0; off < kWBytes; off += 16384)
         bulk_load(smem + kSmemW + off, p.w_image + off, 16384, &bar_w);
     }
     __syncwarp();
+    if (cls == 1 && p.stagger_cycles > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger_cycles) __nanosleep(200);
+    }
     // Chunk c belongs to compute group c & 1, and each group owns its own two-stage ring
     // (stages g and g + 2).  One consumer group per barrier keeps every waiter within one
     // phase of the barrier, which is all a parity wait can disambiguate.
     uint32_t m0 = 0, m1 = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int row0 = (int)(tile * p.tile_rows);
+    for (int tile = 0; tile < my_tiles; ++tile) {
+      const int row0 = first_row + tile * row_step;
       for (int c = 0; c < nc; ++c) {
         const int g = c & 1;
         const uint32_t mg = g ? m1 : m0;
@@ -235,7 +256,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         TC_WAIT(&bar_empty[s], ph ^ 1);
         TRACE(1);
         if (elect_one()) {
-          mbar_expect_tx(&bar_full[s], 2u * (uint32_t)p.tile_rows * 128u);
+          mbar_expect_tx(&bar_full[s], 2u * (uint32_t)trows * 128u);
           uint8_t* dst = smem + kSmemStage + s * kStageBytes;
           tma_load_2d(dst, tm_cur, c * kChunk, row0, &bar_full[s]);
           tma_load_2d(dst + kBoxBytes, tm_prev, c * kChunk, row0, &bar_full[s]);
@@ -260,7 +281,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     auto make64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
     TC_WAIT(&bar_w, 0);
     uint32_t a_cnt0 = 0, a_cnt1 = 0, g_cnt0 = 0, g_cnt1 = 0, ti = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    for (int tile = 0; tile < my_tiles; ++tile, ++ti) {
       // accumulators alias the G buffers of the previous tile: wait until both were drained
       TC_WAIT(&bar_gfree[0], (g_cnt0 & 1) ^ 1);
       TC_WAIT(&bar_gfree[1], (g_cnt1 & 1) ^ 1);
@@ -364,9 +385,10 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     const bool store_leader = (wg == grp) && (quad == 2) && (lane == 0);   // warp 2 / warp 6
     uint32_t a_cnt = 0, g_cnt = 0, ti = 0, sf_base = 0;
     const uint32_t sf_per_tile = (uint32_t)((nc - grp + 1) / 2) - ((((nc - 1) & 1) == grp) ? 1u : 0u);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti, sf_base += sf_per_tile) {
-      const int64_t grow = tile * p.tile_rows + row;
-      const bool row_ok = row < p.tile_rows && grow < p.n;   // lanes beyond the tile carry stale data
+    for (int tile = 0; tile < my_tiles; ++tile, ++ti, sf_base += sf_per_tile) {
+      const int grow32 = first_row + tile * row_step + row;
+      const int64_t grow = grow32;
+      const bool row_ok = row < trows && grow32 < row_limit;   // lanes beyond the tile carry stale data
       uint32_t keep_stage = grp;   // set in phase A whenever has_out
       // pull this thread's 64-byte slice of x towards L2 now; phase B reads it ~10k cycles later
       if (row_ok && wg * 16 < p.d)
@@ -503,7 +525,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
         pair_sync(grp);
         if (store_leader) {
-          const int row0 = (int)(tile * p.tile_rows);
+          const int row0 = first_row + tile * row_step;
           tma_store_2d(tm_prev, out_s, q * kQ, row0);               // rows / columns beyond
           tma_store_2d(tm_prev, out_s + kBoxBytes, q * kQ + 32, row0);  // n, k are clipped
           tma_store_commit();
@@ -655,10 +677,41 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   if (tile_rows > kTileM) tile_rows = kTileM;
   const int64_t ntiles = (a.n + tile_rows - 1) / tile_rows;
   const unsigned grid = (unsigned)(ntiles < S.num_sms ? ntiles : S.num_sms);
-  CUtensorMap tm_za, tm_zb;
+
+  // v1 schedule (see TcParams): two classes of CTAs.  With >= 2 waves the odd CTAs start
+  // `stagger` cycles late and get shorter tiles (measured on B200: all SMs in phase A at once
+  // saturate HBM while it idles during the MMA-bound phases; de-phasing half of the SMs cut
+  // the step from 55.6 to 52.5 us even with the delay simply added on top).
+  int64_t h[2] = {tile_rows, tile_rows};
+  int stagger = 0;
+  const char* st_env = getenv("LASSO_B200_STAGGER");
+  if (version == 1 && waves >= 2 && grid == (unsigned)S.num_sms) {
+    stagger = st_env ? atoi(st_env) : 12000;   // swept on B200 at C2: 0 -> 56.3 us, 8k -> 54.0, 12k -> 51.6, 16k -> 56.9
+    // one row costs ~80 cycles of a tile's HBM share: take stagger / (waves * 80) rows off the
+    // late class per tile and give them to the early class
+    const double h_avg = (double)a.n / (double)(waves * grid);
+    int64_t dh = (int64_t)(stagger / (double)(waves * 80) + 0.5);
+    int64_t h0 = ((int64_t)(h_avg + dh / 2.0 + 0.999) + 7) / 8 * 8;
+    if (h0 > kTileM) h0 = kTileM;
+    const int64_t n_even = ((int64_t)grid + 1) / 2, n_odd = (int64_t)grid / 2;
+    int64_t rest = a.n - n_even * waves * h0;
+    int64_t h1 = rest > 0 ? ((rest + n_odd * waves - 1) / (n_odd * waves) + 7) / 8 * 8 : 8;
+    if (h1 > kTileM) {   // cannot happen for a consistent h_avg, but never drop rows
+      h0 = tile_rows;
+      h1 = tile_rows;
+      stagger = 0;
+    }
+    h[0] = h0;
+    h[1] = h1;
+  }
+  const int64_t n_even = ((int64_t)grid + 1) / 2;
+  const int64_t region_a = n_even * waves * h[0];
+  CUtensorMap tm_za, tm_zb, tm_za1, tm_zb1;
   int rc;
-  if ((rc = make_map(&tm_za, a.z_a, a.n, a.k, (int)tile_rows))) return rc;
-  if ((rc = make_map(&tm_zb, a.z_b, a.n, a.k, (int)tile_rows))) return rc;
+  if ((rc = make_map(&tm_za, a.z_a, a.n, a.k, (int)(version == 1 ? h[0] : tile_rows)))) return rc;
+  if ((rc = make_map(&tm_zb, a.z_b, a.n, a.k, (int)(version == 1 ? h[0] : tile_rows)))) return rc;
+  if ((rc = make_map(&tm_za1, a.z_a, a.n, a.k, (int)h[1]))) return rc;
+  if ((rc = make_map(&tm_zb1, a.z_b, a.n, a.k, (int)h[1]))) return rc;
 
   double t = 1.0;
   for (int it = 0; it < a.maxiter; ++it) {
@@ -671,6 +724,14 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     p.d = a.d;
     p.k = a.k;
     p.tile_rows = (int)tile_rows;
+    p.stagger_cycles = stagger;
+    p.cls_rows[0] = (int)h[0];
+    p.cls_rows[1] = (int)h[1];
+    p.cls_base[0] = 0;
+    p.cls_end[0] = region_a < a.n ? region_a : a.n;
+    p.cls_base[1] = region_a;
+    p.cls_end[1] = a.n;
+    p.waves = (int)waves;
     p.lr = a.lr;
     p.lam = a.lam;
     double beta = 0.0;
@@ -691,7 +752,8 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     const int dsteps = (a.d + 15) / 16;
 #define LASSO_TC_LAUNCH(DS)                                                                \
   do {                                                                                     \
-    if (version == 1) fista_tc_kernel<DS><<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, p);   \
+    if (version == 1)                                                                      \
+      fista_tc_kernel<DS><<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, tm_za1, tm_zb1, p);   \
     else fista_tc2_kernel<DS><<<grid, kThreads2, kSmemBytes, st>>>(tm_za, tm_zb, p);              \
   } while (0)
     switch (dsteps) {
