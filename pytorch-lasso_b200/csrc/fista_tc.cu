@@ -177,6 +177,7 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_full[kStages], bar_empty[kStages];
   __shared__ uint64_t bar_aready[2], bar_sfree[2], bar_rfull, bar_rready, bar_gfull[2], bar_gfree[2];
+  __shared__ uint64_t bar_tdone[2];   // pair p has finished phase C of the current tile
   __shared__ uint32_t tmem_base_s;
   __shared__ double red[16];
 
@@ -217,6 +218,8 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
     }
     mbar_init(&bar_rfull, 1);
     mbar_init(&bar_rready, 512);
+    mbar_init(&bar_tdone[0], 256);
+    mbar_init(&bar_tdone[1], 256);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -436,6 +439,10 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         // Phases of bar_sfree are counted in sf_base: one per chunk of this pair except the
         // tile's very last chunk, which commits to bar_rfull instead.
         if (c >= 2) TC_WAIT(&bar_sfree[grp], (sf_base + (uint32_t)(c >> 1) - 1u) & 1u);
+        // first TMEM store of a tile: the OTHER pair must have finished phase C of the previous
+        // tile (its reads of the y master, and -- having seen every G chunk -- all GEMM2 MMAs
+        // that read the r pieces aliased with the piece stages)
+        else if (ti > 0) TC_WAIT(&bar_tdone[grp ^ 1], (ti - 1) & 1);
         TRACE(22);
         ++a_cnt;
         tc_fence_after();
@@ -538,8 +545,11 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         pair_sync(grp);
         mbar_arrive(&bar_empty[keep_stage]);
       }
-      // y master / r pieces are rewritten by the next tile: all compute warps must be done
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // y master / r pieces are rewritten by the next tile, but only its first TMEM store has to
+      // wait for the other pair (see phase A): the pair that finishes first already loads and
+      // splits its first chunk of the next tile meanwhile
+      tc_fence_before();
+      mbar_arrive(&bar_tdone[grp]);
       TRACE(50);
     }
     if (store_leader) tma_store_wait_all<0>();
