@@ -139,6 +139,30 @@ int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gr
                                         const float* redraw, int32_t* zeroed,
                                         void* stream);
 
+/*
+ * Building blocks of the slow path of ista(): backtrack=True (Beck-Teboulle line search with
+ * batch-global F and Q, ista.py:17-54) and verbose=True (ista.py:80-81).  The host keeps the
+ * reference's per-trial decision (one scalar read-back per trial, like `if F_next <= Q_next`).
+ *
+ *   gradient:  grad[n,k] = (point weight^T - x) weight ;  f_sum[0] = sum (point weight^T - x)^2
+ *              (ista.py:22-24: fval_0 = 0.5 f_sum, fgrad_0 = grad)
+ *   trial:     cand = softshrink(point - step grad, alpha step)          (ista.py:40)
+ *              sums[0] = sum (cand weight^T - x)^2   sums[1] = sum |cand|
+ *              sums[2] = sum (cand - point) grad     sums[3] = sum (cand - point)^2   (ista.py:26-35)
+ *   momentum:  y = z_next + beta (z_next - z) (y may be NULL), delta[0] = sum |z - z_next|
+ *              (ista.py:93, 100)
+ * f_sum / sums / delta are DEVICE pointers to doubles and are overwritten.
+ */
+int32_t lasso_b200_gradient_f32(const float* x, const float* point, const float* weight,
+                                int64_t n, int32_t d, int32_t k, float* grad, double* f_sum,
+                                void* stream);
+int32_t lasso_b200_linesearch_trial_f32(const float* x, const float* point, const float* grad,
+                                        const float* weight, int64_t n, int32_t d, int32_t k,
+                                        double step, double alpha, float* cand, double* sums,
+                                        void* stream);
+int32_t lasso_b200_momentum_f32(const float* z_next, const float* z, double beta, float* y,
+                                int64_t count, double* delta, void* stream);
+
 /* free the per-device private workspace (buffers are re-grown on demand) */
 int32_t lasso_b200_release_workspace(void);
 

@@ -28,6 +28,9 @@ EXPORTS = (
     "lasso_b200_loss_terms_f32",
     "lasso_b200_gram_f32",
     "lasso_b200_dict_update_gram_f32",
+    "lasso_b200_gradient_f32",
+    "lasso_b200_linesearch_trial_f32",
+    "lasso_b200_momentum_f32",
     "lasso_b200_release_workspace",
 )
 
@@ -65,6 +68,12 @@ def _declare(lib):
     lib.lasso_b200_gram_f32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     lib.lasso_b200_dict_update_gram_f32.restype = i32
     lib.lasso_b200_dict_update_gram_f32.argtypes = [vp, vp, vp, i32, i32, f64, vp, vp, vp]
+    lib.lasso_b200_gradient_f32.restype = i32
+    lib.lasso_b200_gradient_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.lasso_b200_linesearch_trial_f32.restype = i32
+    lib.lasso_b200_linesearch_trial_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, f64, f64, vp, vp, vp]
+    lib.lasso_b200_momentum_f32.restype = i32
+    lib.lasso_b200_momentum_f32.argtypes = [vp, vp, f64, vp, i64, vp, vp]
     lib.lasso_b200_release_workspace.restype = i32
     lib.lasso_b200_release_workspace.argtypes = []
 
@@ -220,6 +229,49 @@ def dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None):
             redraw.data_ptr() if redraw is not None else None, zeroed.data_ptr(),
             _stream_ptr(dictionary.device)))
     return zeroed
+
+
+def gradient(x, point, weight, grad_out=None):
+    """(grad[n,k], f_sum device [1] float64) at ``point`` (ista.py:22-24)."""
+    lib = load()
+    x, point, weight = _dev_f32(x, "x"), _dev_f32(point, "point"), _dev_f32(weight, "weight")
+    n, d = x.shape
+    k = weight.shape[1]
+    grad = grad_out if grad_out is not None else torch.empty_like(point)
+    f_sum = torch.empty(1, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.lasso_b200_gradient_f32(x.data_ptr(), point.data_ptr(), weight.data_ptr(), n, d, k,
+                                           grad.data_ptr(), f_sum.data_ptr(), _stream_ptr(x.device)))
+    return grad, f_sum
+
+
+def linesearch_trial(x, point, grad, weight, step, alpha, cand_out=None):
+    """(cand[n,k], sums device [4] float64) for one trial step (ista.py:26-40)."""
+    lib = load()
+    x, point, grad, weight = (_dev_f32(x, "x"), _dev_f32(point, "point"), _dev_f32(grad, "grad"),
+                              _dev_f32(weight, "weight"))
+    n, d = x.shape
+    k = weight.shape[1]
+    cand = cand_out if cand_out is not None else torch.empty_like(point)
+    sums = torch.empty(4, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.lasso_b200_linesearch_trial_f32(
+            x.data_ptr(), point.data_ptr(), grad.data_ptr(), weight.data_ptr(), n, d, k,
+            float(step), float(alpha), cand.data_ptr(), sums.data_ptr(), _stream_ptr(x.device)))
+    return cand, sums
+
+
+def momentum(z_next, z, beta, want_y=True):
+    """(y = z_next + beta (z_next - z) or None, delta device [1] float64 = sum |z - z_next|)."""
+    lib = load()
+    z_next, z = _dev_f32(z_next, "z_next"), _dev_f32(z, "z")
+    y = torch.empty_like(z_next) if want_y else None
+    delta = torch.empty(1, dtype=torch.float64, device=z.device)
+    with torch.cuda.device(z.device):
+        _check(lib.lasso_b200_momentum_f32(z_next.data_ptr(), z.data_ptr(), float(beta),
+                                           y.data_ptr() if want_y else None, z.numel(),
+                                           delta.data_ptr(), _stream_ptr(z.device)))
+    return y, delta
 
 
 def release_workspace():

@@ -352,6 +352,51 @@ int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gr
   return dict_update_run(dict, gram_zz, gram_zx, d, k, eps, redraw, zeroed, (cudaStream_t)stream);
 }
 
+int32_t lasso_b200_gradient_f32(const float* x, const float* point, const float* weight, int64_t n,
+                                int32_t d, int32_t k, float* grad, double* f_sum, void* stream) {
+  t_error[0] = 0;
+  int rc = check_problem(x, weight, grad, n, d, k);
+  if (rc) return rc;
+  if (!f_sum || (n > 0 && !point)) {
+    set_error("null pointer passed to gradient");
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (n == 0) {
+    LASSO_CUDA_TRY(cudaMemsetAsync(f_sum, 0, sizeof(double), (cudaStream_t)stream));
+    return LASSO_B200_OK;
+  }
+  return gradient_run(x, point, weight, n, d, k, grad, f_sum, (cudaStream_t)stream);
+}
+
+int32_t lasso_b200_linesearch_trial_f32(const float* x, const float* point, const float* grad,
+                                        const float* weight, int64_t n, int32_t d, int32_t k,
+                                        double step, double alpha, float* cand, double* sums,
+                                        void* stream) {
+  t_error[0] = 0;
+  int rc = check_problem(x, weight, cand, n, d, k);
+  if (rc) return rc;
+  if (!sums || (n > 0 && (!point || !grad)) || !(step > 0.0)) {
+    set_error("invalid argument to linesearch_trial");
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (n == 0) {
+    LASSO_CUDA_TRY(cudaMemsetAsync(sums, 0, 4 * sizeof(double), (cudaStream_t)stream));
+    return LASSO_B200_OK;
+  }
+  return trial_run(x, point, grad, weight, n, d, k, (float)step, (float)(alpha * step), cand, sums,
+                   (cudaStream_t)stream);
+}
+
+int32_t lasso_b200_momentum_f32(const float* z_next, const float* z, double beta, float* y,
+                                int64_t count, double* delta, void* stream) {
+  t_error[0] = 0;
+  if (count < 0 || !delta || (count > 0 && (!z_next || !z))) {
+    set_error("invalid argument to momentum");
+    return LASSO_B200_ERR_INVALID;
+  }
+  return momentum_run(z_next, z, (float)beta, y, count, delta, (cudaStream_t)stream);
+}
+
 int32_t lasso_b200_release_workspace(void) {
   std::lock_guard<std::mutex> lock(g_ws_mutex);
   Workspace* ws = nullptr;

@@ -106,6 +106,12 @@ int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double
                   cudaStream_t st);
 int loss_terms_run(const float* x, const float* z, const float* w, int64_t n, int d, int k,
                    double* out, cudaStream_t st);
+int gradient_run(const float* x, const float* point, const float* w, int64_t n, int d, int k,
+                 float* grad, double* f_terms, cudaStream_t st);
+int trial_run(const float* x, const float* point, const float* grad, const float* w, int64_t n,
+              int d, int k, float step, float lam, float* cand, double* sums4, cudaStream_t st);
+int momentum_run(const float* z_next, const float* z, float beta, float* y, int64_t count,
+                 double* delta, cudaStream_t st);
 int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz,
              double* gzx, cudaStream_t st);
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,

@@ -61,10 +61,15 @@ struct StepParams {
   int use_prev;  // 0: Y = z_cur (first iteration or plain ISTA)
   int mode;      // 0: FISTA step, 1: loss terms (sum r^2, sum |z|) into out2
   double* out2;
+  const float* aux;  // MODE 3: gradient at z_cur
+  float* out;        // MODE 3: candidate code
   StepCtl ctl;
 };
 
-// MODE 0 = iteration step, MODE 1 = loss terms only.
+// MODE 0 = iteration step, MODE 1 = loss terms only,
+// MODE 2 = gradient: z_io <- (z_cur W^T - x) W, out2[0] += sum r^2            (ista.py:22-24)
+// MODE 3 = line-search trial: cand = softshrink(z_cur - lr * aux, lam) -> out,  (ista.py:40)
+//          out2 += { sum (cand W^T - x)^2, sum |cand|, sum dz * aux, sum dz^2 } (ista.py:26-35)
 template <int TM, int MODE>
 __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
   constexpr int RPT = TM / 16;  // rows per thread
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
   float* Rs = smem;                                   // [TM][r_ld]
   float* As = Rs + TM * r_ld;                         // [TM][kCk + kPad]   (Y chunk)
   float* Ws = As + TM * (kCk + kPad);                 // max([kBlk][kCk+kPad], [kCk][kBlk+kPad])
-  __shared__ double red[kThreads / 32][2];
+  __shared__ double red[kThreads / 32][4];
 
   if (MODE == 0 && p.ctl.tol_abs >= 0.0 && p.ctl.iter >= 1 &&
       p.ctl.hist[p.ctl.iter - 1] <= p.ctl.tol_abs)
@@ -85,7 +90,8 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
   const bool kvec = (p.k & 3) == 0;
   const bool dvec = (p.d & 3) == 0;
   const int64_t ntiles = (p.n + TM - 1) / TM;
-  double acc_a = 0.0, acc_b = 0.0;  // MODE 0: delta ; MODE 1: sum r^2, sum |z|
+  double acc_a = 0.0, acc_b = 0.0;  // MODE 0: delta ; MODE 1/2/3: sum r^2, sum |z|
+  double acc_c = 0.0, acc_d = 0.0;  // MODE 3: sum dz*g, sum dz^2
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TM;
@@ -111,7 +117,23 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
             zc.z = momentum_point(zc.z, zp.z, p.beta);
             zc.w = momentum_point(zc.w, zp.w, p.beta);
           }
-          if (MODE == 1 && db == 0)
+          if (MODE == 3) {
+            const float4 g = ld4(p.aux, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+            float4 cd;
+            cd.x = ista_update(zc.x, g.x, p.lr, p.lam);
+            cd.y = ista_update(zc.y, g.y, p.lr, p.lam);
+            cd.z = ista_update(zc.z, g.z, p.lr, p.lam);
+            cd.w = ista_update(zc.w, g.w, p.lr, p.lam);
+            if (db == 0) {
+              st4(p.out, row0 + r, j0 + c4, p.n, p.k, p.k, kvec, cd);
+              const float dx = __fsub_rn(cd.x, zc.x), dy = __fsub_rn(cd.y, zc.y);
+              const float dz = __fsub_rn(cd.z, zc.z), dw = __fsub_rn(cd.w, zc.w);
+              acc_c += (double)dx * g.x + (double)dy * g.y + (double)dz * g.z + (double)dw * g.w;
+              acc_d += (double)dx * dx + (double)dy * dy + (double)dz * dz + (double)dw * dw;
+            }
+            zc = cd;
+          }
+          if ((MODE == 1 || MODE == 3) && db == 0)
             acc_b += (double)(fabsf(zc.x) + fabsf(zc.y)) + (double)(fabsf(zc.z) + fabsf(zc.w));
           *reinterpret_cast<float4*>(&As[r * (kCk + kPad) + c4]) = zc;
         }
@@ -151,10 +173,10 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
           float v = 0.f;
           if (gr < p.n && i < p.d) v = __fsub_rn(acc[r][c], p.x[gr * p.d + i]);
           if (i < d_pad) Rs[lr_ * r_ld + i] = v;
-          if (MODE == 1) acc_a += (double)v * (double)v;
+          if (MODE != 0) acc_a += (double)v * (double)v;
         }
     }
-    if (MODE == 1) continue;
+    if (MODE == 1 || MODE == 3) continue;
 
     // ---------------- phase 2: G = R W, fused update ----------------------
     for (int j0 = 0; j0 < p.k; j0 += kBlk) {
@@ -209,6 +231,11 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
         const int64_t gr = row0 + ty * RPT + r;
         const int col = j0 + tx * 4;
         if (gr >= p.n || col >= p.k) continue;
+        if (MODE == 2) {   // gradient only
+          st4(p.z_io, gr, col, p.n, p.k, p.k, kvec,
+              make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+          continue;
+        }
         float4 zc = ld4(p.z_cur, gr, col, p.n, p.k, p.k, kvec);
         float4 y = zc;
         if (p.use_prev) {
@@ -234,26 +261,58 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
     (void)dvec;
   }
 
-  // block reduction -> one double atomic per CTA
+  // block reduction -> one double atomic per CTA and output
   acc_a = warp_sum(acc_a);
   acc_b = warp_sum(acc_b);
+  acc_c = warp_sum(acc_c);
+  acc_d = warp_sum(acc_d);
   if ((tid & 31) == 0) {
     red[tid >> 5][0] = acc_a;
     red[tid >> 5][1] = acc_b;
+    red[tid >> 5][2] = acc_c;
+    red[tid >> 5][3] = acc_d;
   }
   __syncthreads();
   if (tid == 0) {
-    double sa = 0.0, sb = 0.0;
+    double sa = 0.0, sb = 0.0, sc = 0.0, sd = 0.0;
     for (int wi = 0; wi < kThreads / 32; ++wi) {
       sa += red[wi][0];
       sb += red[wi][1];
+      sc += red[wi][2];
+      sd += red[wi][3];
     }
     if (MODE == 0) {
       if (p.ctl.hist) atomicAdd(&p.ctl.hist[p.ctl.iter], sa);
     } else {
       atomicAdd(&p.out2[0], sa);
-      atomicAdd(&p.out2[1], sb);
+      if (MODE != 2) atomicAdd(&p.out2[1], sb);
+      if (MODE == 3) {
+        atomicAdd(&p.out2[2], sc);
+        atomicAdd(&p.out2[3], sd);
+      }
     }
+  }
+}
+
+// y = z_next + beta (z_next - z) (ista.py:100) and delta = sum |z - z_next| (ista.py:93)
+__global__ void momentum_kernel(const float* __restrict__ z_next, const float* __restrict__ z,
+                                float beta, float* __restrict__ y, int64_t count,
+                                double* __restrict__ delta) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float zn = z_next[i], zo = z[i];
+    if (y) y[i] = momentum_point(zn, zo, beta);
+    acc += (double)fabsf(__fsub_rn(zo, zn));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) s += red[wi];
+    atomicAdd(delta, s);
   }
 }
 
@@ -369,6 +428,55 @@ int loss_terms_run(const float* x, const float* z, const float* w, int64_t n, in
   p.ctl.tol_abs = -1.0;
   p.ctl.iter = 0;
   return dispatch<1>(p, st);
+}
+
+int gradient_run(const float* x, const float* point, const float* w, int64_t n, int d, int k,
+                 float* grad, double* f_terms, cudaStream_t st) {
+  LASSO_CUDA_TRY(cudaMemsetAsync(f_terms, 0, sizeof(double), st));
+  StepParams p{};
+  p.x = x;
+  p.w = w;
+  p.z_cur = point;
+  p.z_io = grad;
+  p.n = n;
+  p.d = d;
+  p.k = k;
+  p.mode = 2;
+  p.out2 = f_terms;
+  p.ctl.tol_abs = -1.0;
+  return dispatch<2>(p, st);
+}
+
+int trial_run(const float* x, const float* point, const float* grad, const float* w, int64_t n,
+              int d, int k, float step, float lam, float* cand, double* sums4, cudaStream_t st) {
+  LASSO_CUDA_TRY(cudaMemsetAsync(sums4, 0, 4 * sizeof(double), st));
+  StepParams p{};
+  p.x = x;
+  p.w = w;
+  p.z_cur = point;
+  p.aux = grad;
+  p.out = cand;
+  p.n = n;
+  p.d = d;
+  p.k = k;
+  p.lr = step;
+  p.lam = lam;
+  p.mode = 3;
+  p.out2 = sums4;
+  p.ctl.tol_abs = -1.0;
+  return dispatch<3>(p, st);
+}
+
+int momentum_run(const float* z_next, const float* z, float beta, float* y, int64_t count,
+                 double* delta, cudaStream_t st) {
+  LASSO_CUDA_TRY(cudaMemsetAsync(delta, 0, sizeof(double), st));
+  if (count == 0) return LASSO_B200_OK;
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  momentum_kernel<<<blocks, 256, 0, st>>>(z_next, z, beta, y, count, delta);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  return LASSO_B200_OK;
 }
 
 }  // namespace lasso

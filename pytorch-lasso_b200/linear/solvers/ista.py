@@ -9,13 +9,21 @@ between iterations).  Differences, all deliberate:
   the host (ista.py:8-14); the reference value itself varies ~1e-6 run to run.
 * the batch-global stop test (ista.py:93) is evaluated on the device; kernels
   of later iterations turn into no-ops once it fires.
+* ``backtrack=True`` (ista.py:17-54) and ``verbose=True`` (ista.py:80-81) take a
+  slower path: the host drives one iteration at a time -- like the reference,
+  whose line search branches on the host after every trial -- but every
+  arithmetic step is a kernel of the library (gradient, trial, momentum, loss).
 * CPU tensors go through the C ABI's host entry point (H2D, solve, D2H) -- the
   arithmetic always runs on the GPU.  There is no PyTorch fallback.
-* extra keyword ``path`` ('auto' | 'ffma' | 'tcgen05') selects the kernel, and
+* extra keywords: ``path`` ('auto' | 'ffma' | 'tcgen05') selects the kernel,
   ``group`` a torch.distributed process group whose ranks hold row shards of one
-  batch (the stop test is then made global with one deferred all-reduce).
+  batch (the stop test is then made global with one deferred all-reduce), ``out``
+  a preallocated result buffer.
 """
 from __future__ import annotations
+
+import math
+import warnings
 
 import numpy as np
 import torch
@@ -68,9 +76,16 @@ def _first_stop(hist: torch.Tensor, tol_abs: float) -> int:
     return int(hits[0]) + 1 if hits.numel() else int(hist.numel())
 
 
+def _global(values: torch.Tensor, group):
+    """Sum a small device tensor of partial sums over the shards, return python floats."""
+    if group is not None and torch.distributed.get_world_size(group) > 1:
+        torch.distributed.all_reduce(values, group=group)
+    return [float(v) for v in values.tolist()]
+
+
 def solve(x, z0, weight, alpha=1.0, fast=True, lr='auto', maxiter=10, tol=1e-5,
           path='auto', group=None, return_iters=False, out=None):
-    """Shared implementation: ``z0`` may be None for the all-zero start; ``out`` is an
+    """Fast path (constant step): ``z0`` may be None for the all-zero start; ``out`` is an
     optional preallocated [n,k] float32 result buffer on x's device."""
     _validate(x, z0, weight)
     n, k = x.shape[0], weight.shape[1]
@@ -112,20 +127,91 @@ def solve(x, z0, weight, alpha=1.0, fast=True, lr='auto', maxiter=10, tol=1e-5,
     return (z, done) if return_iters else z
 
 
+def _backtracking(point, x, weight, alpha, lr0, eta, group, maxiter=1000, verbose=False):
+    """Beck-Teboulle line search with batch-global F and Q (ista.py:17-54); one scalar
+    read-back per trial, exactly where the reference branches on the host."""
+    grad, f_sum = _cabi.gradient(x, point, weight)
+    (f_sum0,) = _global(f_sum, group)
+    fval0 = 0.5 * f_sum0
+    step = lr0
+    cand = None
+    for i in range(maxiter):
+        cand, sums = _cabi.linesearch_trial(x, point, grad, weight, step, alpha, cand_out=cand)
+        r2, l1, dzg, dz2 = _global(sums, group)
+        big_f = 0.5 * r2 + alpha * l1
+        big_q = fval0 + dzg + (0.5 / step) * dz2 + alpha * l1
+        if verbose:
+            print('iter: %4d,  t: %0.5f,  F-Q: %0.5f' % (i, step, big_f - big_q))
+        if big_f <= big_q:
+            return cand, step
+        step = step / eta
+    warnings.warn('backtracking line search failed. Reverting to initial '
+                  'step size')
+    cand, _ = _cabi.linesearch_trial(x, point, grad, weight, lr0, alpha, cand_out=cand)
+    return cand, lr0
+
+
+def _solve_stepwise(x, z0, weight, alpha, fast, lr, maxiter, tol, backtrack, eta_backtrack,
+                    verbose, group):
+    """Host-driven loop for backtrack / verbose (one iteration at a time, ista.py:79-102)."""
+    _validate(x, z0, weight)
+    if not x.is_cuda:
+        dev = _utils.default_device()
+        z = _solve_stepwise(x.to(dev), z0.to(dev), weight.to(dev), alpha, fast, lr, maxiter, tol,
+                            backtrack, eta_backtrack, verbose, group)
+        return z.cpu()
+    if lr == 'auto':
+        lr = 1.0 / lipschitz_constant(weight)
+    lr, alpha = float(lr), float(alpha)
+    numel = z0.numel()
+    n_rows = x.shape[0]
+    if group is not None and torch.distributed.get_world_size(group) > 1:
+        cnt = torch.tensor([numel, n_rows], dtype=torch.int64, device=x.device)
+        torch.distributed.all_reduce(cnt, group=group)
+        numel, n_rows = int(cnt[0]), int(cnt[1])
+    tol_abs = _abs_tolerance(numel, tol)
+
+    z = z0.contiguous()
+    y, t = z, 1
+    for _ in range(maxiter):
+        if verbose:
+            r2, l1 = _global(_cabi.loss_terms(x, z, weight), group)
+            print('loss: %0.4f' % ((0.5 * r2 + alpha * l1) / n_rows))
+        point = y if fast else z
+        if backtrack:
+            z_next, _ = _backtracking(point, x, weight, alpha, lr, eta_backtrack, group)
+        else:
+            grad, _ = _cabi.gradient(x, point, weight)
+            z_next, _ = _cabi.linesearch_trial(x, point, grad, weight, lr, alpha)
+        beta = 0.0
+        if fast:
+            t_next = (1 + math.sqrt(1 + 4 * t ** 2)) / 2
+            beta = (t - 1) / t_next
+        y_next, delta = _cabi.momentum(z_next, z, beta, want_y=fast)
+        (delta,) = _global(delta, group)
+        if delta <= tol_abs:
+            z = z_next
+            break
+        if fast:
+            y, t = y_next, t_next
+        z = z_next
+    return z
+
+
 def ista(x, z0, weight, alpha=1.0, fast=True, lr='auto', maxiter=10,
          tol=1e-5, backtrack=False, eta_backtrack=1.5, verbose=False,
          path='auto', group=None, out=None):
     """Drop-in for ``lasso.linear.solvers.ista`` (ista.py:57-104)."""
-    if backtrack:
-        if eta_backtrack <= 1:
-            raise ValueError('eta must be > 1.')  # ista.py:18-19
-        raise NotImplementedError(
-            "backtrack=True (ista.py:17-54) is not implemented in lasso_b200 yet")
-    if verbose:
-        raise NotImplementedError(
-            "verbose=True (per-iteration loss print, ista.py:80-81) is not implemented; "
-            "use linear.lasso_loss on the result")
     if maxiter == 0:
         return z0  # the reference returns the z0 object itself
+    if backtrack or verbose:
+        if backtrack and eta_backtrack <= 1:
+            raise ValueError('eta must be > 1.')  # ista.py:18-19
+        z = _solve_stepwise(x, z0, weight, alpha, fast, lr, maxiter, tol, backtrack,
+                            eta_backtrack, verbose, group)
+        if out is not None:
+            out.copy_(z)
+            return out
+        return z
     return solve(x, z0, weight, alpha=alpha, fast=fast, lr=lr, maxiter=maxiter, tol=tol,
                  path=path, group=group, out=out)
