@@ -74,6 +74,8 @@ struct TcParams {
   int64_t cls_base[2], cls_end[2];
   int waves;
   int stagger_cycles;
+  // L2 eviction priorities (TMA cache hints) of the two code buffers, see fista_tc_run
+  uint64_t pol_cur, pol_prev;
   StepCtl ctl;
   volatile int* dbg;       // host-mapped debug record or nullptr
   unsigned long long* trace;  // LASSO_B200_TRACE: per-warp (clock << 8 | event) log of block 0
@@ -261,8 +263,8 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         if (elect_one()) {
           mbar_expect_tx(&bar_full[s], 2u * (uint32_t)trows * 128u);
           uint8_t* dst = smem + kSmemStage + s * kStageBytes;
-          tma_load_2d(dst, tm_cur, c * kChunk, row0, &bar_full[s]);
-          tma_load_2d(dst + kBoxBytes, tm_prev, c * kChunk, row0, &bar_full[s]);
+          tma_load_2d_hint(dst, tm_cur, c * kChunk, row0, &bar_full[s], p.pol_cur);
+          tma_load_2d_hint(dst + kBoxBytes, tm_prev, c * kChunk, row0, &bar_full[s], p.pol_prev);
         }
         __syncwarp();
       }
@@ -533,8 +535,8 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
         pair_sync(grp);
         if (store_leader) {
           const int row0 = first_row + tile * row_step;
-          tma_store_2d(tm_prev, out_s, q * kQ, row0);               // rows / columns beyond
-          tma_store_2d(tm_prev, out_s + kBoxBytes, q * kQ + 32, row0);  // n, k are clipped
+          tma_store_2d_hint(tm_prev, out_s, q * kQ, row0, p.pol_prev);               // rows / columns
+          tma_store_2d_hint(tm_prev, out_s + kBoxBytes, q * kQ + 32, row0, p.pol_prev);  // beyond n, k are clipped
           tma_store_commit();
         }
         TRACE(41);
@@ -735,6 +737,17 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     p.k = a.k;
     p.tile_rows = (int)tile_rows;
     p.stagger_cycles = stagger;
+    // L2 residency: the two code buffers and x (151 MB at C2) cycle through a 126 MB L2, which
+    // a plain LRU turns into 100 % misses.  Buffer A is therefore always accessed with
+    // evict-last priority and buffer B with evict-first: A stays resident (reads and in-place
+    // writes hit L2), only B streams through HBM.
+    {
+      const char* l2_env = getenv("LASSO_B200_L2PIN");
+      const bool pin = !(l2_env && l2_env[0] == '0');
+      const uint64_t pol_a = pin ? kEvictLast : kEvictNormal, pol_b = pin ? kEvictFirst : kEvictNormal;
+      p.pol_cur = p.cur_is_a ? pol_a : pol_b;
+      p.pol_prev = p.cur_is_a ? pol_b : pol_a;
+    }
     p.cls_rows[0] = (int)h[0];
     p.cls_rows[1] = (int)h[1];
     p.cls_base[0] = 0;
