@@ -40,9 +40,14 @@ typedef enum lasso_b200_status {
 
 /* which inner-loop kernel lasso_b200_fista_f32 uses */
 typedef enum lasso_b200_path {
-  LASSO_B200_PATH_AUTO = 0,   /* tcgen05 kernel when the shape fits, else FFMA      */
-  LASSO_B200_PATH_FFMA = 1,   /* CUDA-core fp32 FFMA kernel: any n, d, k            */
-  LASSO_B200_PATH_TCGEN05 = 2 /* tcgen05 / TMEM tensor-core kernel (split bf16x3)   */
+  LASSO_B200_PATH_AUTO = 0,    /* resident tcgen05 kernel when the shape fits, else FFMA     */
+  LASSO_B200_PATH_FFMA = 1,    /* CUDA-core fp32 FFMA kernel: any n, d, k                    */
+  LASSO_B200_PATH_TCGEN05 = 2, /* streaming tcgen05 kernel, one launch per iteration (bf16x3) */
+  LASSO_B200_PATH_RESIDENT = 3 /* resident tcgen05 kernel: all iterations of a 128-row tile on
+                                  chip in ONE launch (fp16x2 operand split of the rescaled
+                                  problem).  Synchronises the stream once per solve; falls
+                                  back to LASSO_B200_PATH_TCGEN05 by itself if an iterate
+                                  leaves the fp16 operand range.                               */
 } lasso_b200_path;
 
 /* ABI version: major*1000 + minor */
@@ -57,6 +62,9 @@ int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k);
 /* number of kernels this library has launched in this process (bench: gpu_launches) */
 int64_t lasso_b200_launch_count(void);
 
+/* number of resident solves that had to be redone by the streaming kernel (fp16 range) */
+int64_t lasso_b200_resident_fallbacks(void);
+
 /*
  * ISTA / FISTA solve -- replaces the loop of lasso/linear/solvers/ista.py:57-104
  * (gradient step ista.py:71-73,90; stop test ista.py:64,93-95; momentum
@@ -70,7 +78,10 @@ int64_t lasso_b200_launch_count(void);
  *   maxiter        >= 0;  0 copies z0 (or zeros) to z_out
  *   fast           non-zero = FISTA momentum
  *   tol_abs        absolute threshold of the batch-global stop test, i.e. the
- *                  reference's z0.numel()*tol.  Negative disables the test.
+ *                  reference's z0.numel()*tol.  Negative disables the test.  The
+ *                  streaming paths evaluate it on the device (later launches turn
+ *                  into no-ops); the resident path records every iteration's sum
+ *                  and replays a shorter run when the test fired before maxiter.
  *   iters_done     optional HOST pointer: number of iterations executed (forces
  *                  one stream synchronisation when non-NULL)
  *   delta_hist     optional DEVICE pointer to maxiter doubles: sum|z_i - z_{i+1}|

@@ -14,14 +14,16 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblasso_b200.so")
 
-PATH_AUTO, PATH_FFMA, PATH_TCGEN05 = 0, 1, 2
-_PATH_NAMES = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tcgen05": PATH_TCGEN05}
+PATH_AUTO, PATH_FFMA, PATH_TCGEN05, PATH_RESIDENT = 0, 1, 2, 3
+_PATH_NAMES = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tcgen05": PATH_TCGEN05,
+               "resident": PATH_RESIDENT}
 
 EXPORTS = (
     "lasso_b200_version",
     "lasso_b200_last_error",
     "lasso_b200_select_path",
     "lasso_b200_launch_count",
+    "lasso_b200_resident_fallbacks",
     "lasso_b200_fista_f32",
     "lasso_b200_fista_f32_host",
     "lasso_b200_lipschitz_f32",
@@ -54,6 +56,8 @@ def _declare(lib):
     lib.lasso_b200_select_path.argtypes = [i64, i32, i32]
     lib.lasso_b200_launch_count.restype = i64
     lib.lasso_b200_launch_count.argtypes = []
+    lib.lasso_b200_resident_fallbacks.restype = i64
+    lib.lasso_b200_resident_fallbacks.argtypes = []
     lib.lasso_b200_fista_f32.restype = i32
     lib.lasso_b200_fista_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, f64, f64, i32, i32,
                                          f64, c.POINTER(i32), vp, i32, vp]
@@ -124,6 +128,10 @@ def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
 
 def launch_count() -> int:
     return int(load().lasso_b200_launch_count())
+
+
+def resident_fallbacks() -> int:
+    return int(load().lasso_b200_resident_fallbacks())
 
 
 def select_path(n: int, d: int, k: int) -> int:

@@ -3,12 +3,14 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
 namespace lasso {
 
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_res_fallbacks{0};   // resident solves redone by the streaming kernel
 static thread_local char t_error[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -134,7 +136,10 @@ const char* lasso_b200_last_error(void) { return t_error; }
 
 int64_t lasso_b200_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int64_t lasso_b200_resident_fallbacks(void) { return (int64_t)g_res_fallbacks.load(); }
+
 int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k) {
+  if (fista_res_supported(n, d, k)) return LASSO_B200_PATH_RESIDENT;
   return fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
 }
 
@@ -150,12 +155,14 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
     return LASSO_B200_ERR_INVALID;
   }
   if (path == LASSO_B200_PATH_AUTO) path = lasso_b200_select_path(n, d, k);
-  if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05) {
+  if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05 &&
+      path != LASSO_B200_PATH_RESIDENT) {
     set_error("unknown path %d", path);
     return LASSO_B200_ERR_INVALID;
   }
-  if (path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) {
-    set_error("tcgen05 path does not take n=%lld d=%d k=%d", (long long)n, d, k);
+  if ((path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) ||
+      (path == LASSO_B200_PATH_RESIDENT && !fista_res_supported(n, d, k))) {
+    set_error("tcgen05 paths do not take n=%lld d=%d k=%d", (long long)n, d, k);
     return LASSO_B200_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -181,6 +188,53 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
   if ((rc = ensure(ws->ctl, 256))) return rc;
 
+  double* hist = (double*)ws->hist.ptr;
+  const float lr_f = (float)lr;               // torch rounds the python scalar to the tensor dtype
+  const float lam_f = (float)(alpha * lr);    // softshrink lambda = alpha*lr, product in double (ista.py:90)
+
+  if (path == LASSO_B200_PATH_RESIDENT) {
+    // All iterations on chip (fista_res.cu).  The stop test is batch-global, so it is taken
+    // afterwards from the recorded sums: when it fired before maxiter the run is replayed with
+    // exactly that many iterations (deterministic kernel => same codes as stopping in place).
+    // If an iterate leaves the fp16 operand range the batch is solved again by the streaming
+    // bf16x3 kernel below.  Both need z0 intact, so an aliased z0 is stashed first.
+    const float* z_start = z0;
+    if (z0 != nullptr && z0 == z_out) {
+      LASSO_CUDA_TRY(cudaMemcpyAsync(ws->code.ptr, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
+      z_start = (const float*)ws->code.ptr;
+    }
+    const bool need_hist = tol_abs >= 0.0 || delta_hist != nullptr;
+    int run_iters = maxiter, fell_back = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+      rc = fista_res_run(x, weight, z_start, z_out, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
+                         need_hist ? hist : nullptr, &fell_back, st);
+      if (rc) return rc;
+      if (fell_back || pass == 1 || tol_abs < 0.0 || run_iters <= 1) break;
+      std::vector<double> h((size_t)run_iters);
+      LASSO_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+      LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+      int done = run_iters;
+      for (int i = 0; i + 1 < run_iters; ++i)
+        if (h[(size_t)i] <= tol_abs) {
+          done = i + 1;
+          break;
+        }
+      if (done == run_iters) break;
+      run_iters = done;
+    }
+    if (!fell_back) {
+      if (delta_hist)
+        LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, hist, sizeof(double) * (size_t)maxiter,
+                                       cudaMemcpyDeviceToDevice, st));
+      if (iters_done) *iters_done = run_iters;
+      return LASSO_B200_OK;
+    }
+    g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
+    z0 = z_start;
+    path = LASSO_B200_PATH_TCGEN05;
+  }
+
   // z_i lives in (i even ? z_a : z_b); put z_maxiter into z_out without a copy
   float* wsbuf = (float*)ws->code.ptr;
   float* z_a = (maxiter & 1) ? wsbuf : z_out;
@@ -188,7 +242,6 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_a, 0, code_bytes, st));
   else if (z0 != z_a)
     LASSO_CUDA_TRY(cudaMemcpyAsync(z_a, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
-  double* hist = (double*)ws->hist.ptr;
   LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
 
   FistaArgs a{};
@@ -199,8 +252,8 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   a.n = n;
   a.d = d;
   a.k = k;
-  a.lr = (float)lr;               // torch rounds the python scalar to the tensor dtype
-  a.lam = (float)(alpha * lr);    // softshrink lambda = alpha*lr, product in double (ista.py:90)
+  a.lr = lr_f;
+  a.lam = lam_f;
   a.maxiter = maxiter;
   a.fast = fast ? 1 : 0;
   a.tol_abs = tol_abs;

@@ -98,7 +98,22 @@ struct FistaArgs {
   double* hist;  // [maxiter] device, zero-initialised
 };
 
+// scale factors of the resident kernel (fista_res.cu): all powers of two
+struct ResScalars {
+  float sx;    // x' = sx x
+  float sw;    // W' = sw W
+  float sz;    // z' = sz z   (sz = sx / sw)
+  float uz;    // z  = uz z'
+  float lr;    // lr / sw^2
+  float lam;   // lam sz
+  int bad;     // inputs not finite / scaled step not representable
+};
+
 int fista_ffma_run(const FistaArgs& a, float* z_out, cudaStream_t st);
+bool fista_res_supported(int64_t n, int d, int k);
+int fista_res_run(const float* x, const float* w, const float* z0, float* z_out, int64_t n, int d,
+                  int k, float lr, float lam, int iters, int fast, double* hist, int* fell_back,
+                  cudaStream_t st);
 bool fista_tc_supported(int64_t n, int d, int k);
 int fista_tc_run(const FistaArgs& a, float* z_out, cudaStream_t st);
 

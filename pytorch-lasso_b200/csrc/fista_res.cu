@@ -1,0 +1,683 @@
+// Resident tcgen05 FISTA for sm_100a: ALL iterations of a 128-row tile run on chip.
+//
+// The streaming kernel (fista_tc.cu) moves n (d + 3k) floats through HBM per iteration and is
+// bound by that traffic.  Rows are independent lasso problems (ista.py:71-73, 90), so a tile
+// can run every iteration without leaving the SM: per call HBM sees x once, z0 once and the
+// final codes once.  What bounds the kernel is then the tensor pipe and the CUDA-core
+// epilogues, which is why the operands are split differently here:
+//
+//   operands  fp32 -> two fp16 pieces  v = h + l  (h = rn16(v), l = rn16(v - h); |v - h - l| <=
+//             2^-22 |v|), three tcgen05.mma kind::f16 products per k-step (h h', h l', l h')
+//             instead of the six of the bf16x3 split.  fp16 has a narrow exponent range, so
+//             the problem is rescaled by powers of two first (max|x| -> [64,128), max|W| ->
+//             [8,16), codes by their ratio): exact, the iterates are bit-for-bit the scaled
+//             iterates of the unscaled problem, and the low pieces stay normal numbers.  An
+//             iterate that would overflow fp16 anyway raises a flag and the caller re-runs
+//             the batch with the streaming bf16x3 kernel.
+//   state     z_i  : shared memory, 128 x 256 fp32, XOR-swizzled rows (128 KB)
+//             y_i  : TMEM columns [0,256) fp32 (the momentum point, ista.py:100)
+//             x    : shared memory 128 x 64 fp32 (32 KB);  dictionary pieces: 64 KB
+//   per iteration (one tile, 16 compute warps = 4 groups of 128 rows, 1 MMA warp):
+//     A   y chunk (32 atoms) -> pieces -> TMEM stage           | GEMM1  R = Y W^T  (TS MMAs,
+//     B   r = (R_big + R_small) - x -> pieces -> TMEM          |         B = resident W, K-major)
+//     C   z+ = softshrink(y - lr g, lam) (ista.py:90), delta,  | GEMM2  G = r W per 64 atoms
+//         y+ = z+ + beta (z+ - z) (ista.py:100), in place      |         (same image, MN-major)
+//   TMEM columns: y 256 | piece stages 2 x 32 | r pieces 64 | acc0 64 | acc1 64 = 512.
+//   The stop test (ista.py:93) cannot be taken mid-run (it is a batch-global sum): every
+//   iteration's sum goes to hist[] and the caller replays a shorter run when it fired early.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lasso {
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileM = 128;
+constexpr int kDP = 64;            // padded d
+constexpr int kKP = 256;           // padded k
+constexpr int kThreadsR = 544;     // warp 0: MMA issuer, warps 1..16: compute
+constexpr uint32_t kSlabBytes = kDP * 128;                 // [64 features][128 B] = 64 atoms of one piece
+constexpr uint32_t kPieceBytes = (kKP / 64) * kSlabBytes;  // 32 KB
+constexpr uint32_t kWBytes = 2 * kPieceBytes;              // 64 KB: h image, l image
+constexpr uint32_t kSmemW = 0;
+constexpr uint32_t kSmemZ = kSmemW + kWBytes;              // [128][256] fp32, 1 KB rows
+constexpr uint32_t kSmemX = kSmemZ + kTileM * kKP * 4;     // [128][64] fp32, 256 B rows
+constexpr uint32_t kSmemBytesR = kSmemX + kTileM * kDP * 4;   // 229376
+
+constexpr uint32_t kColY = 0;
+constexpr uint32_t kColStage = 256;   // stage s: [h 16 cols][l 16 cols] at 256 + 32 s
+constexpr uint32_t kColR = 320;       // r pieces: [h 32 cols][l 32 cols]
+constexpr uint32_t kColAcc0 = 384;    // R_big   / G buffer 0
+constexpr uint32_t kColAcc1 = 448;    // R_small / G buffer 1
+constexpr uint32_t kTmemCols = 512;
+
+constexpr float kPieceLimit = 32768.0f;   // |operand| beyond this: fall back (fp16 max 65504)
+
+struct ResParams {
+  const uint8_t* w_image;   // kWBytes, scaled fp16 pieces
+  const float* x;           // [n][d]
+  const float* z0;          // [n][k] or nullptr
+  float* z_out;             // [n][k]
+  int64_t n;
+  int d, k;
+  int trows;                // rows per tile (<= 128)
+  int ntiles;
+  int iters;
+  const float* beta;        // [iters] momentum coefficient applied at the END of iteration i
+  const ResScalars* scal;
+  double* hist;             // [iters] sum |z_i - z_{i+1}| or nullptr
+  int* flag;                // set to 1 when an operand left the fp16 range
+  volatile int* dbg;        // host-mapped debug record or nullptr
+  unsigned long long* trace;   // LASSO_B200_TRACE: per-warp (clock << 8 | event) log of block 0
+  float limit;              // |operand| at which the solve is handed to the streaming kernel
+};
+
+__device__ __noinline__ void res_wait_slow_path(uint64_t& t0, volatile int* dbg, int line, uint32_t parity) {
+  const uint64_t now = global_timer_ns();
+  if (t0 == 0) {
+    t0 = now;
+    return;
+  }
+  if (now - t0 < 4000000000ull) return;
+  if (dbg) {
+    dbg[1] = line; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x; dbg[4] = -1; dbg[5] = (int)parity;
+    __threadfence_system();
+    dbg[0] = 1;
+    __threadfence_system();
+  }
+  __trap();
+}
+#define RES_WAIT(bar, parity)                                                             \
+  do {                                                                                    \
+    const uint32_t _addr = smem_u32(bar), _par = (parity) & 1u;                           \
+    uint32_t _ok, _n = 0;                                                                 \
+    uint64_t _t0 = 0;                                                                     \
+    for (;;) {                                                                            \
+      asm volatile(                                                                       \
+          "{\n\t.reg .pred P;\n\t"                                                       \
+          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"                  \
+          "selp.b32 %0, 1, 0, P;\n\t}\n"                                                   \
+          : "=r"(_ok)                                                                     \
+          : "r"(_addr), "r"(_par), "r"(20000u)                                            \
+          : "memory");                                                                    \
+      if (_ok) break;                                                                     \
+      if ((++_n & 1023u) == 0) res_wait_slow_path(_t0, p.dbg, __LINE__, _par);            \
+    }                                                                                     \
+  } while (0)
+
+// timeline instrumentation (block 0, lane 0 of every warp, iterations 3 and 4 of its first
+// tile), enabled with LASSO_B200_TRACE=<file>
+#define RTRACE(id)                                                                        \
+  do {                                                                                    \
+    if (p.trace != nullptr && tr_on && (threadIdx.x & 31) == 0 && tr_n < 126)             \
+      p.trace[(threadIdx.x >> 5) * 128 + tr_n++] = ((unsigned long long)clock64() << 8) | (id); \
+  } while (0)
+
+__device__ __forceinline__ float2 rsub2(float2 a, float2 b) {   // a - b, one rounding each
+  return __ffma2_rn(make_float2(-1.f, -1.f), b, a);
+}
+// fp32 pair -> packed fp16 pieces (element .x in the low half = lower k index)
+__device__ __forceinline__ void split2_pair(float2 v, uint32_t& wh, uint32_t& wl) {
+  const __half2 h = __floats2half2_rn(v.x, v.y);
+  const float2 r = rsub2(v, __half22float2(h));   // exact: h is v rounded to 11 bits
+  const __half2 l = __floats2half2_rn(r.x, r.y);
+  wh = *reinterpret_cast<const uint32_t*>(&h);
+  wl = *reinterpret_cast<const uint32_t*>(&l);
+}
+// byte offset of (row, 16-byte chunk c) in the swizzled z tile (1 KB rows) / x tile (256 B rows)
+__device__ __forceinline__ uint32_t z_off(uint32_t row, uint32_t chunk) {
+  return row * 1024u + ((chunk ^ (row & 7u)) << 4);
+}
+__device__ __forceinline__ uint32_t x_off(uint32_t row, uint32_t chunk) {
+  return row * 256u + ((chunk ^ (row & 7u)) << 4);
+}
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int kDSteps>
+__global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_w, bar_aready[2], bar_sfree[2][2], bar_rfull, bar_rready, bar_gfull[2], bar_gfree[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nq = (p.k + 63) >> 6;    // 64-atom chunks (GEMM2 / phase C)
+  const int nc = 2 * nq;             // 32-atom chunks (phase A / GEMM1 k-slices)
+  const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int iters = p.iters;
+
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_aready[b], 128);
+      mbar_init(&bar_sfree[b][0], 1);
+      mbar_init(&bar_sfree[b][1], 1);
+      mbar_init(&bar_gfull[b], 1);
+      mbar_init(&bar_gfree[b], 256);
+    }
+    mbar_init(&bar_rfull, 1);
+    mbar_init(&bar_rready, 512);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== MMA issuer (whole warp runs the control flow) =====================
+    if (elect_one()) {
+      mbar_expect_tx(&bar_w, kWBytes);
+      for (uint32_t off = 0; off < kWBytes; off += 16384)
+        bulk_load(smem + kSmemW + off, p.w_image + off, 16384, &bar_w);
+    }
+    __syncwarp();
+    const uint32_t idesc1 = make_idesc(kFmtF16, 128, kDP, 0, 0);   // B K-major  (GEMM1, N = 64 features)
+    const uint32_t idesc2 = make_idesc(kFmtF16, 128, 64, 0, 1);    // B MN-major (GEMM2, N = 64 atoms)
+    const uint32_t w_addr = smem_u32(smem + kSmemW);
+    const uint64_t desc1 = make_smem_desc_sw128(w_addr, 0, 1024);
+    const uint64_t desc2 = make_smem_desc_sw128(w_addr, kSlabBytes, 1024);
+    const uint32_t d1_lo = (uint32_t)desc1, d1_hi = (uint32_t)(desc1 >> 32);
+    const uint32_t d2_lo = (uint32_t)desc2, d2_hi = (uint32_t)(desc2 >> 32);
+    constexpr uint32_t kPiece16 = kPieceBytes >> 4;
+    auto make64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    RES_WAIT(&bar_w, 0);
+    uint32_t gi = 0;                 // global iteration counter (over tiles)
+    uint32_t a_cnt0 = 0, a_cnt1 = 0;   // completions of bar_aready[s] consumed
+    uint32_t g_iss0 = 0, g_iss1 = 0;   // G chunks issued to buffer b
+    int tr_n = 0;
+    for (int tile = 0; tile < my_tiles; ++tile) {
+      for (int it = 0; it < iters; ++it, ++gi) {
+        const bool tr_on = blockIdx.x == 0 && tile == 0 && (it == 3 || it == 4);
+        // ---- GEMM1: accumulators alias the G buffers: both must have been drained ----
+        if (g_iss0) RES_WAIT(&bar_gfree[0], g_iss0 - 1);
+        if (g_iss1) RES_WAIT(&bar_gfree[1], g_iss1 - 1);
+        RTRACE(10);
+        tc_fence_after();
+        for (int c = 0; c < nc; ++c) {
+          const int s = c & 1;
+          if (s == 0) {
+            RES_WAIT(&bar_aready[0], a_cnt0);
+            ++a_cnt0;
+          } else {
+            RES_WAIT(&bar_aready[1], a_cnt1);
+            ++a_cnt1;
+          }
+          RTRACE(11);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t t_stage = tbase + kColStage + s * 32;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t koff = (uint32_t)(c >> 1) * (kSlabBytes >> 4) + (uint32_t)((c & 1) * 4 + ks * 2);
+              const uint32_t acc_on = (c > 0 || ks > 0) ? 1u : 0u;
+              const uint64_t qh = make64(d1_lo + koff, d1_hi);
+              const uint64_t ql = make64(d1_lo + koff + kPiece16, d1_hi);
+              const uint32_t ah = t_stage + ks * 8, al = ah + 16;
+              mma_ts<false>(tbase + kColAcc1, ah, ql, idesc1, acc_on);   // small products
+              mma_ts<false>(tbase + kColAcc1, al, qh, idesc1, 1);
+              mma_ts<false>(tbase + kColAcc0, ah, qh, idesc1, acc_on);   // leading product
+            }
+            // stage `s` is used nq times per iteration (use j = c >> 1); the "consumed" signal
+            // of use j goes to barrier [s][j & 1], so that each barrier has a single group of
+            // waiters that observes its completions in order (a parity wait cannot tell
+            // phases two apart)
+            mma_commit(&bar_sfree[s][(c >> 1) & 1]);
+            if (c == nc - 1) mma_commit(&bar_rfull);
+          }
+          __syncwarp();
+          RTRACE(12);
+        }
+        // ---- GEMM2 ----
+        RES_WAIT(&bar_rready, gi);
+        RTRACE(14);
+        tc_fence_after();
+        for (int q = 0; q < nq; ++q) {
+          const int b = q & 1;
+          if (b == 0) {
+            if (q >= 2) RES_WAIT(&bar_gfree[0], g_iss0 - 1);
+            ++g_iss0;
+          } else {
+            if (q >= 2) RES_WAIT(&bar_gfree[1], g_iss1 - 1);
+            ++g_iss1;
+          }
+          RTRACE(15);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t t_acc = tbase + (b ? kColAcc1 : kColAcc0);
+            const uint32_t t_r = tbase + kColR;
+            const uint32_t qoff = (uint32_t)q * (kSlabBytes >> 4);
+            uint32_t acc_on = 0;
+            // small products first (l h', h l'), leading product last
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+#pragma unroll
+              for (int ks = 0; ks < kDSteps; ++ks) {
+                const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
+                mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
+                acc_on = 1;
+              }
+            }
+            mma_commit(&bar_gfull[b]);
+          }
+          __syncwarp();
+          RTRACE(16);
+        }
+      }
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant of this warp
+    const int wg = (warp - 1) >> 2;            // group 0..3 (128 rows each)
+    const int grp = wg & 1;                    // pair: owns G buffer grp / chunks q = grp, grp + 2
+    const int half = wg >> 1;                  // which 32 atoms of a 64-atom chunk; piece stage
+    const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
+    const int ct = tid - 32;                   // 0..511
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t* zs = smem + kSmemZ;
+    uint8_t* xs = smem + kSmemX;
+    const ResScalars sc = *p.scal;
+    const float2 lr2 = make_float2(sc.lr, sc.lr);
+    const float lam = sc.lam;
+    float amax = 0.f;
+    int tr_n = 0;
+    bool tr_on = false;
+    uint32_t gi = 0;
+    uint32_t g_cnt = 0;                        // completions of bar_gfull[grp] consumed
+    // this group writes uses j = grp, grp + 2 of piece stage `half`; before use j >= 1 it waits
+    // for the consumption of use j - 1, signalled on bar_sfree[half][(j - 1) & 1], which
+    // completes (nq + 1 - e) / 2 times per iteration (e = (j - 1) & 1 = grp ^ 1)
+    const uint32_t sf_e = (uint32_t)(grp ^ 1);
+    const uint32_t sf_per_it = ((uint32_t)nq + 1u - sf_e) >> 1;
+
+    // A: y chunk q (this thread's 32 atoms) -> fp16 pieces -> piece stage `half`
+    auto phase_a = [&](int q, const uint32_t (&yv)[32]) {
+      uint32_t wh[16], wl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        split2_pair(make_float2(__uint_as_float(yv[2 * j]), __uint_as_float(yv[2 * j + 1])), wh[j], wl[j]);
+      // stage free?  use j = q of this iteration; the first use needs no wait (everybody saw
+      // GEMM1 of the previous iteration complete through bar_rfull)
+      RTRACE(21);
+      if (q > 0) RES_WAIT(&bar_sfree[half][sf_e], gi * sf_per_it + (((uint32_t)q - 1u) >> 1));
+      RTRACE(22);
+      tc_fence_after();
+      const uint32_t t_stage = tbase + lane_base + kColStage + half * 32;
+      tmem_st16(t_stage, wh);
+      tmem_st16(t_stage + 16, wl);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bar_aready[half]);
+      RTRACE(23);
+    };
+
+    for (int tile = 0; tile < my_tiles; ++tile) {
+      const int64_t row0 = (int64_t)(blockIdx.x + (int64_t)tile * gridDim.x) * p.trows;
+      int valid = p.trows;
+      if (row0 + valid > p.n) valid = (int)(p.n - row0);
+      // ---------------- load the tile: x and z0, rescaled ----------------
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = ct + i * 512, r = idx >> 4, c4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < valid && c4 * 4 < p.d) {
+          v = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.d + c4 * 4));
+          v.x *= sc.sx; v.y *= sc.sx; v.z *= sc.sx; v.w *= sc.sx;
+        }
+        *reinterpret_cast<float4*>(xs + x_off(r, c4)) = v;
+      }
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.z0 != nullptr && r < valid && c4 * 4 < p.k) {
+          v = __ldg(reinterpret_cast<const float4*>(p.z0 + (row0 + r) * p.k + c4 * 4));
+          v.x *= sc.sz; v.y *= sc.sz; v.z *= sc.sz; v.w *= sc.sz;
+        }
+        *reinterpret_cast<float4*>(zs + z_off(r, c4)) = v;
+      }
+      compute_sync();
+      // ---------------- y_0 = z_0 (ista.py:76), first phase A ----------------
+      for (int q = grp; q < nq; q += 2) {
+        uint32_t yv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 z4 = *reinterpret_cast<const float4*>(zs + z_off(row, q * 16 + half * 8 + j));
+          yv[4 * j + 0] = __float_as_uint(z4.x);
+          yv[4 * j + 1] = __float_as_uint(z4.y);
+          yv[4 * j + 2] = __float_as_uint(z4.z);
+          yv[4 * j + 3] = __float_as_uint(z4.w);
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(z4.x), fabsf(z4.y)), fmaxf(fabsf(z4.z), fabsf(z4.w))));
+        }
+        tmem_st32(tbase + lane_base + kColY + q * 64 + half * 32, yv);
+        phase_a(q, yv);
+      }
+
+      for (int it = 0; it < iters; ++it) {
+        tr_on = blockIdx.x == 0 && tile == 0 && (it == 3 || it == 4);
+        const float beta = __ldg(p.beta + it);
+        const float2 beta2 = make_float2(beta, beta);
+        // ---------------- phase B: r = R - x -> pieces (16 features per thread) ----------------
+        {
+          float4 xv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(xs + x_off(row, wg * 4 + j));
+          RES_WAIT(&bar_rfull, gi);
+          RTRACE(30);
+          tc_fence_after();
+          uint32_t rb[16], rs[16];
+          tmem_ld16(tbase + lane_base + kColAcc0 + wg * 16, rb);
+          tmem_ld16(tbase + lane_base + kColAcc1 + wg * 16, rs);
+          tmem_wait_ld();
+          uint32_t wh[8], wl[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 ra = rsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 0]), __uint_as_float(rb[4 * j + 1])),
+                                               make_float2(__uint_as_float(rs[4 * j + 0]), __uint_as_float(rs[4 * j + 1]))),
+                                    make_float2(xv[j].x, xv[j].y));
+            const float2 rc = rsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3])),
+                                               make_float2(__uint_as_float(rs[4 * j + 2]), __uint_as_float(rs[4 * j + 3]))),
+                                    make_float2(xv[j].z, xv[j].w));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(ra.x), fabsf(ra.y)), fmaxf(fabsf(rc.x), fabsf(rc.y))));
+            split2_pair(ra, wh[2 * j], wl[2 * j]);
+            split2_pair(rc, wh[2 * j + 1], wl[2 * j + 1]);
+          }
+          const uint32_t t_r = tbase + lane_base + kColR + wg * 8;
+          tmem_st8(t_r, wh);
+          tmem_st8(t_r + 32, wl);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_rready);
+          RTRACE(31);
+        }
+        // ---------------- phase C: fused update, in place ----------------
+        float part = 0.f;
+        for (int q = grp; q < nq; q += 2) {
+          RES_WAIT(&bar_gfull[grp], g_cnt);
+          RTRACE(40);
+          ++g_cnt;
+          tc_fence_after();
+          uint32_t g[32], yv[32];
+          tmem_ld32(tbase + lane_base + (grp ? kColAcc1 : kColAcc0) + half * 32, g);
+          tmem_ld32(tbase + lane_base + kColY + q * 64 + half * 32, yv);
+          tmem_wait_ld();
+          tc_fence_before();
+          mbar_arrive(&bar_gfree[grp]);   // accumulator is in registers: hand the buffer back
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint8_t* zp = zs + z_off(row, q * 16 + half * 8 + j);
+            const float4 z4 = *reinterpret_cast<const float4*>(zp);
+            float2 zo[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const float2 yy = make_float2(__uint_as_float(yv[4 * j + 2 * h2]), __uint_as_float(yv[4 * j + 2 * h2 + 1]));
+              const float2 gg = make_float2(__uint_as_float(g[4 * j + 2 * h2]), __uint_as_float(g[4 * j + 2 * h2 + 1]));
+              const float2 zz = h2 ? make_float2(z4.z, z4.w) : make_float2(z4.x, z4.y);
+              // softshrink(y - lr g, lam): v - clamp(v, +-lam) (bit-identical to the three-way select)
+              const float2 v = rsub2(yy, __fmul2_rn(lr2, gg));
+              const float2 c = make_float2(fminf(fmaxf(v.x, -lam), lam), fminf(fmaxf(v.y, -lam), lam));
+              const float2 zn = rsub2(v, c);
+              const float2 dl = rsub2(zn, zz);                       // z+ - z
+              part += fabsf(dl.x) + fabsf(dl.y);                     // stop-test sum (ista.py:93)
+              const float2 yn = __fadd2_rn(zn, __fmul2_rn(beta2, dl));   // ista.py:100
+              amax = fmaxf(amax, fmaxf(fabsf(yn.x), fabsf(yn.y)));
+              zo[h2] = zn;
+              yv[4 * j + 2 * h2] = __float_as_uint(yn.x);
+              yv[4 * j + 2 * h2 + 1] = __float_as_uint(yn.y);
+            }
+            *reinterpret_cast<float4*>(zp) = make_float4(zo[0].x, zo[0].y, zo[1].x, zo[1].y);
+          }
+          tmem_st32(tbase + lane_base + kColY + q * 64 + half * 32, yv);
+          tmem_wait_st();
+          RTRACE(41);
+        }
+        if (p.hist != nullptr) {
+          float s = part;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) atomicAdd(p.hist + it, (double)s * (double)sc.uz);
+        }
+        ++gi;
+        // ---------------- phase A of the next iteration ----------------
+        if (it + 1 < iters) {
+          for (int q = grp; q < nq; q += 2) {
+            uint32_t yv[32];
+            tmem_ld32(tbase + lane_base + kColY + q * 64 + half * 32, yv);
+            tmem_wait_ld();
+            RTRACE(20);
+            phase_a(q, yv);
+          }
+        }
+      }
+      // ---------------- store the codes ----------------
+      compute_sync();
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
+        if (r < valid && c4 * 4 < p.k) {
+          float4 v = *reinterpret_cast<const float4*>(zs + z_off(r, c4));
+          v.x *= sc.uz; v.y *= sc.uz; v.z *= sc.uz; v.w *= sc.uz;
+          *reinterpret_cast<float4*>(p.z_out + (row0 + r) * p.k + c4 * 4) = v;
+        }
+      }
+      compute_sync();
+    }
+    if (!(amax < p.limit)) atomicExch(p.flag, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, kTmemCols);
+}
+
+// ---- set-up kernels ---------------------------------------------------------------------
+// max |x|, max |W| as float bit patterns (non-negative floats order like unsigned ints);
+// a NaN / inf anywhere ends up as a huge pattern and is caught by res_setup_kernel
+__global__ void res_amax_kernel(const float* __restrict__ x, int64_t nx, const float* __restrict__ w, int nw,
+                                unsigned* __restrict__ out) {
+  unsigned m = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += stride)
+    m = max(m, __float_as_uint(x[i]) & 0x7FFFFFFFu);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out + 0, m);
+  if (blockIdx.x == 0) {
+    unsigned mw = 0;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) mw = max(mw, __float_as_uint(w[i]) & 0x7FFFFFFFu);
+    mw = __reduce_max_sync(0xffffffffu, mw);
+    if ((threadIdx.x & 31) == 0 && mw) atomicMax(out + 1, mw);
+  }
+}
+
+// scale factors (powers of two), scaled step / threshold, momentum table, flag reset
+__global__ void res_setup_kernel(const unsigned* __restrict__ amax, float lr, float lam, int iters, int fast,
+                                 ResScalars* __restrict__ sc, float* __restrict__ beta, int* __restrict__ flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float ax = __uint_as_float(amax[0]), aw = __uint_as_float(amax[1]);
+  int bad = 0;
+  int ex = 0, ew = 0;
+  if (!(ax < 3.0e38f) || !(aw < 3.0e38f)) bad = 1;
+  if (ax > 0.f && !bad) ex = 6 - ilogbf(ax);    // max |x'| in [64, 128)
+  if (aw > 0.f && !bad) ew = 3 - ilogbf(aw);    // max |W'| in [8, 16)
+  ex = max(-100, min(100, ex));
+  ew = max(-40, min(40, ew));
+  sc->sx = ldexpf(1.f, ex);
+  sc->sw = ldexpf(1.f, ew);
+  sc->sz = ldexpf(1.f, ex - ew);
+  sc->uz = ldexpf(1.f, ew - ex);
+  sc->lr = ldexpf(lr, -2 * ew);
+  sc->lam = ldexpf(lam, ex - ew);
+  if (!(sc->lr > 0.f) || !(sc->lr < 3.0e38f) || !(sc->lam < 3.0e38f) || (lam > 0.f && !(sc->lam > 0.f))) bad = 1;
+  sc->bad = bad;
+  *flag = bad;
+  // momentum: python floats of ista.py:77-78, 98-101 (t0 = 1; beta_i = (t_i - 1) / t_{i+1})
+  double t = 1.0;
+  for (int i = 0; i < iters; ++i) {
+    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
+    beta[i] = fast ? (float)((t - 1.0) / t_next) : 0.f;
+    t = t_next;
+  }
+}
+
+// dictionary [d][k] fp32 -> two scaled fp16 piece images, each [k/64 slabs][64 rows][128 B] with
+// the 128-byte swizzle; zero padded to d = 64, k = 256
+__global__ void res_prep_w_kernel(const float* __restrict__ w, int d, int k, const ResScalars* __restrict__ sc,
+                                  uint8_t* __restrict__ image) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kDP * kKP) return;
+  const int i = idx / kKP, j = idx % kKP;
+  const float v = (i < d && j < k) ? w[(int64_t)i * k + j] * sc->sw : 0.f;
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  const uint32_t off = (uint32_t)(j / 64) * kSlabBytes + sw128_offset(i, (j % 64) * 2);
+  *reinterpret_cast<__half*>(image + off) = h;
+  *reinterpret_cast<__half*>(image + kPieceBytes + off) = l;
+}
+
+struct ResState {
+  uint8_t* w_image = nullptr;
+  ResScalars* scal = nullptr;
+  unsigned* amax = nullptr;
+  int* flag = nullptr;
+  float* beta = nullptr;
+  int beta_cap = 0;
+  int num_sms = 0;
+  bool attr_set = false;
+  int* dbg_host = nullptr;
+  int* dbg_dev = nullptr;
+  unsigned long long* trace = nullptr;
+};
+ResState g_res[64];
+
+}  // namespace
+
+bool fista_res_supported(int64_t n, int d, int k) {
+  return n >= 1 && d >= 4 && d <= kDP && k >= 4 && k <= kKP && (d % 4) == 0 && (k % 4) == 0 &&
+         n < (int64_t)1 << 31;
+}
+
+// Runs `iters` iterations from z0 (nullptr = zeros) into z_out.  *fell_back = 1 when an operand
+// left the fp16 range (z_out is then unspecified and the caller must use another path).
+// Synchronises the stream once (to read that flag).
+int fista_res_run(const float* x, const float* w, const float* z0, float* z_out, int64_t n, int d, int k,
+                  float lr, float lam, int iters, int fast, double* hist, int* fell_back, cudaStream_t st) {
+  int dev = 0;
+  LASSO_CUDA_TRY(cudaGetDevice(&dev));
+  ResState& S = g_res[dev];
+  if (!S.w_image) {
+    LASSO_CUDA_TRY(cudaMalloc(&S.w_image, kWBytes));
+    LASSO_CUDA_TRY(cudaMalloc(&S.scal, sizeof(ResScalars)));
+    LASSO_CUDA_TRY(cudaMalloc(&S.amax, 2 * sizeof(unsigned)));
+    LASSO_CUDA_TRY(cudaMalloc(&S.flag, sizeof(int)));
+    LASSO_CUDA_TRY(cudaDeviceGetAttribute(&S.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (iters > S.beta_cap) {
+    if (S.beta) LASSO_CUDA_TRY(cudaFree(S.beta));
+    S.beta = nullptr;
+    S.beta_cap = 0;
+    const int cap = iters < 1024 ? 1024 : iters;
+    LASSO_CUDA_TRY(cudaMalloc(&S.beta, sizeof(float) * (size_t)cap));
+    S.beta_cap = cap;
+  }
+  if (!S.dbg_host && getenv("LASSO_B200_DEBUG")) {
+    LASSO_CUDA_TRY(cudaHostAlloc((void**)&S.dbg_host, 4096, cudaHostAllocMapped));
+    memset(S.dbg_host, 0, 4096);
+    LASSO_CUDA_TRY(cudaHostGetDevicePointer((void**)&S.dbg_dev, S.dbg_host, 0));
+  }
+  const char* trace_path = getenv("LASSO_B200_TRACE");
+  if (trace_path && !S.trace) LASSO_CUDA_TRY(cudaMalloc(&S.trace, 32 * 128 * 8));
+  if (S.trace) LASSO_CUDA_TRY(cudaMemsetAsync(S.trace, 0, 32 * 128 * 8, st));
+  if (!S.attr_set) {
+    const void* kernels[4] = {(const void*)fista_res_kernel<1>, (const void*)fista_res_kernel<2>,
+                              (const void*)fista_res_kernel<3>, (const void*)fista_res_kernel<4>};
+    for (const void* kfn : kernels)
+      LASSO_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesR));
+    S.attr_set = true;
+  }
+  LASSO_CUDA_TRY(cudaMemsetAsync(S.amax, 0, 2 * sizeof(unsigned), st));
+  {
+    const int64_t nx = n * d;
+    int blocks = (int)((nx + 256 * 16 - 1) / (256 * 16));
+    if (blocks > S.num_sms * 8) blocks = S.num_sms * 8;
+    if (blocks < 1) blocks = 1;
+    res_amax_kernel<<<blocks, 256, 0, st>>>(x, nx, w, d * k, S.amax);
+    LASSO_CHECK_LAUNCH();
+    res_setup_kernel<<<1, 32, 0, st>>>(S.amax, lr, lam, iters, fast, S.scal, S.beta, S.flag);
+    LASSO_CHECK_LAUNCH();
+    res_prep_w_kernel<<<(kDP * kKP + 255) / 256, 256, 0, st>>>(w, d, k, S.scal, S.w_image);
+    LASSO_CHECK_LAUNCH();
+    count_launch(3);
+  }
+  // tile height: smallest multiple of 8 rows that keeps the number of waves of 128-row tiles
+  const int64_t slots = S.num_sms;
+  const int64_t waves = ((n + kTileM - 1) / kTileM + slots - 1) / slots;
+  int64_t trows = (n + waves * slots - 1) / (waves * slots);
+  trows = ((trows + 7) / 8) * 8;
+  if (trows > kTileM) trows = kTileM;
+  const int64_t ntiles = (n + trows - 1) / trows;
+  const unsigned grid = (unsigned)(ntiles < S.num_sms ? ntiles : S.num_sms);
+
+  ResParams p{};
+  p.w_image = S.w_image;
+  p.x = x;
+  p.z0 = z0;
+  p.z_out = z_out;
+  p.n = n;
+  p.d = d;
+  p.k = k;
+  p.trows = (int)trows;
+  p.ntiles = (int)ntiles;
+  p.iters = iters;
+  p.beta = S.beta;
+  p.scal = S.scal;
+  p.hist = hist;
+  p.flag = S.flag;
+  p.dbg = S.dbg_dev;
+  p.trace = trace_path ? S.trace : nullptr;
+  p.limit = kPieceLimit;
+  if (const char* lim = getenv("LASSO_B200_RES_LIMIT")) p.limit = (float)atof(lim);   // tests: force the fallback
+  switch ((d + 15) / 16) {
+    case 1: fista_res_kernel<1><<<grid, kThreadsR, kSmemBytesR, st>>>(p); break;
+    case 2: fista_res_kernel<2><<<grid, kThreadsR, kSmemBytesR, st>>>(p); break;
+    case 3: fista_res_kernel<3><<<grid, kThreadsR, kSmemBytesR, st>>>(p); break;
+    default: fista_res_kernel<4><<<grid, kThreadsR, kSmemBytesR, st>>>(p); break;
+  }
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  int flag = 0;
+  cudaError_t e = cudaMemcpyAsync(&flag, S.flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (S.dbg_host && S.dbg_host[0]) {
+    set_error("resident kernel barrier timeout: line %d block %d thread %d parity %d (%s)", S.dbg_host[1],
+              S.dbg_host[2], S.dbg_host[3], S.dbg_host[5], cudaGetErrorString(e));
+    return LASSO_B200_ERR_CUDA;
+  }
+  if (e != cudaSuccess) {
+    set_error("resident kernel failed: %s", cudaGetErrorString(e));
+    return LASSO_B200_ERR_CUDA;
+  }
+  if (S.trace && trace_path) {
+    static unsigned long long host_trace[32 * 128];
+    LASSO_CUDA_TRY(cudaMemcpy(host_trace, S.trace, sizeof(host_trace), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int w = 0; w < 32; ++w)
+        for (int i = 0; i < 128 && host_trace[w * 128 + i]; ++i)
+          fprintf(f, "%d %llu %llu\n", w, host_trace[w * 128 + i] >> 8, host_trace[w * 128 + i] & 255);
+      fclose(f);
+    }
+  }
+  *fell_back = flag;
+  return LASSO_B200_OK;
+}
+
+}  // namespace lasso

@@ -10,7 +10,8 @@ n, d, k = 65536, 64, 256
 x, w = make_problem(n, d, k, seed=0)
 lr = 1.0 / oracle.lipschitz_constant(w)
 dev = torch.device("cuda", 0)
-_cabi.fista_device(x.to(dev), w.to(dev), None, 0.1, lr, 6, True, 0.0, path="tcgen05")
+kpath = os.environ.get("TRACE_PATH", "tcgen05")   # "resident": iterations 3 and 4 of block 0's first tile
+_cabi.fista_device(x.to(dev), w.to(dev), None, 0.1, lr, 6, True, -1.0, path=kpath)
 torch.cuda.synchronize()
 ev = collections.defaultdict(list)
 for line in open(path):
@@ -19,7 +20,11 @@ t0 = min(t for v in ev.values() for t, _ in v)
 names = {1: "P:empty_ok", 10: "M:tile", 11: "M:aready_ok", 12: "M:commit_chunk", 13: "M:commit_rfull", 14: "M:rready_ok",
          15: "M:gfree_ok", 16: "M:commit_g", 20: "C:full_ok", 21: "C:math_done", 22: "C:sfree_ok", 23: "C:st_done",
          30: "C:rfull_ok", 31: "C:phaseB_done", 40: "C:gfull_ok", 41: "C:epi_done", 50: "C:tile_end"}
-for wi in [int(v) for v in os.environ.get("TRACE_WARPS", "0,2,4,12").split(",")]:
+if kpath == "resident":
+    names = {10: "M:acc_free", 11: "M:aready_ok", 12: "M:commit_chunk", 14: "M:rready_ok", 15: "M:gfree_ok",
+             16: "M:commit_g", 20: "A:y_loaded", 21: "A:split_done", 22: "A:stage_free", 23: "A:arrived",
+             30: "B:rfull_ok", 31: "B:done", 40: "C:gfull_ok", 41: "C:chunk_done"}
+for wi in [int(v) for v in os.environ.get("TRACE_WARPS", "0,2,4,12" if kpath != "resident" else "0,1,5,9,13").split(",")]:
     print("---- warp", wi)
     prev = None
     for t, e in ev[wi][:int(os.environ.get("TRACE_ROWS", "70"))]:
