@@ -42,7 +42,10 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("LASSO_B200_BUILD_TRACE"):   # per-warp timeline instrumentation (tools/tc_trace.py)
+        flags.append("-DLASSO_RES_TRACE")
+    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -204,11 +204,13 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
       z_start = (const float*)ws->code.ptr;
     }
     const bool need_hist = tol_abs >= 0.0 || delta_hist != nullptr;
+    // a threshold of exactly 0 only asks whether anything moved; the sums are not needed then
+    const int hist_mode = !need_hist ? 0 : ((delta_hist == nullptr && tol_abs == 0.0) ? 2 : 1);
     int run_iters = maxiter, fell_back = 0;
     for (int pass = 0; pass < 2; ++pass) {
       if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
       rc = fista_res_run(x, weight, z_start, z_out, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
-                         need_hist ? hist : nullptr, &fell_back, st);
+                         need_hist ? hist : nullptr, hist_mode, &fell_back, st);
       if (rc) return rc;
       if (fell_back || pass == 1 || tol_abs < 0.0 || run_iters <= 1) break;
       std::vector<double> h((size_t)run_iters);

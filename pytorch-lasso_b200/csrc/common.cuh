@@ -112,8 +112,8 @@ struct ResScalars {
 int fista_ffma_run(const FistaArgs& a, float* z_out, cudaStream_t st);
 bool fista_res_supported(int64_t n, int d, int k);
 int fista_res_run(const float* x, const float* w, const float* z0, float* z_out, int64_t n, int d,
-                  int k, float lr, float lam, int iters, int fast, double* hist, int* fell_back,
-                  cudaStream_t st);
+                  int k, float lr, float lam, int iters, int fast, double* hist, int hist_mode,
+                  int* fell_back, cudaStream_t st);
 bool fista_tc_supported(int64_t n, int d, int k);
 int fista_tc_run(const FistaArgs& a, float* z_out, cudaStream_t st);
 

@@ -23,8 +23,9 @@ names = {1: "P:empty_ok", 10: "M:tile", 11: "M:aready_ok", 12: "M:commit_chunk",
 if kpath == "resident":
     names = {10: "M:acc_free", 11: "M:aready_ok", 12: "M:commit_chunk", 14: "M:rready_ok", 15: "M:gfree_ok",
              16: "M:commit_g", 20: "A:y_loaded", 21: "A:split_done", 22: "A:stage_free", 23: "A:arrived",
-             30: "B:rfull_ok", 31: "B:done", 40: "C:gfull_ok", 41: "C:chunk_done"}
-for wi in [int(v) for v in os.environ.get("TRACE_WARPS", "0,2,4,12" if kpath != "resident" else "0,1,5,9,13").split(",")]:
+             30: "B:rfull_ok", 31: "B:done", 40: "C:gfull_ok", 41: "C:chunk_done", 42: "C:gfree_arrived",
+             17: "M:gfree0_ok", 18: "M:iter_top"}
+for wi in [int(v) for v in os.environ.get("TRACE_WARPS", "0,2,4,12" if kpath != "resident" else "16,0,4,8,12").split(",")]:
     print("---- warp", wi)
     prev = None
     for t, e in ev[wi][:int(os.environ.get("TRACE_ROWS", "70"))]:
