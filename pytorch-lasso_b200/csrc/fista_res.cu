@@ -52,11 +52,11 @@ constexpr uint32_t kSmemZ = kSmemW + kWBytes;              // [128][256] fp32, 1
 constexpr uint32_t kSmemX = kSmemZ + kTileM * kKP * 4;     // [128][64] fp32, 256 B rows
 constexpr uint32_t kSmemBytesR = kSmemX + kTileM * kDP * 4;   // 229376
 
-constexpr uint32_t kColY = 0;
-constexpr uint32_t kColStage = 256;   // stage s: [h 16 cols][l 16 cols] at 256 + 32 s
-constexpr uint32_t kColR = 320;       // r pieces: [h 32 cols][l 32 cols]
-constexpr uint32_t kColAcc0 = 384;    // R_big   / G buffer 0
-constexpr uint32_t kColAcc1 = 448;    // R_small / G buffer 1
+constexpr uint32_t kColY = 0;         // y, fp32
+constexpr uint32_t kColStage = 256;   // piece slot S: [h 32 cols][l 32 cols] = 64 atoms of y
+constexpr uint32_t kColR = 320;       // r pieces: [h 32 cols][l 32 cols] = 64 features
+constexpr uint32_t kColAccR = 384;    // R = Y W^T (GEMM1)
+constexpr uint32_t kColAccG = 448;    // G = r W, one 64-atom chunk (GEMM2)
 constexpr uint32_t kTmemCols = 512;
 
 constexpr float kPieceLimit = 32768.0f;   // |operand| beyond this: fall back (fp16 max 65504)
@@ -153,43 +153,35 @@ __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 512;"
 // Schedule of one iteration (NQ = 4 chunks of 64 atoms; all 16 compute warps work on the same
 // chunk, each thread on 16 atoms of one row):
 //
-//   MMA warp   GEMM2 q0 | q1 | q2 | q3 ........ GEMM1 slices q0 | q1 | q2 | q3 ... (B) GEMM2 ...
-//   compute         C(0)   | C(1)   | C(2)   | C(3)   | late piece stores | idle | B |
+//   MMA warp   GEMM2 q0 | q1 | G1' q0 | GEMM2 q2 | G1' q1 | GEMM2 q3 | G1' q2 | G1' q3 ... (B) GEMM2 q0
+//   compute          C(0)     |    C(1)     |    C(2)     |    C(3)     | idle |   B   | idle
 //
-// C(q): z+ = softshrink(y - lr g, lam), delta sum, y+ = z+ + beta (z+ - z) in place, then the
-// fp16 pieces of y+ for the next iteration's GEMM1.  The pieces of q0 go to slot S_A (dedicated
-// TMEM columns) at once and those of q1 to slot S_B, which aliases the r pieces and becomes
-// writable when GEMM2 is complete (bar_g2done) -- about when C(1) ends.  GEMM1 may start after
-// the g-load of C(3) (its accumulators alias the G buffers), finds q0 and q1 staged, and frees
-// the slots for q2 / q3, whose pieces wait in registers until then.  Every barrier except the
-// per-buffer / per-slot ones completes exactly once per iteration, so its phase is the
-// iteration parity.
+// C(q): z+ = softshrink(y - lr g, lam), stop-test record, y+ = z+ + beta (z+ - z) in place, then
+// the fp16 pieces of y+ go to the piece slot S, where the slice q of the NEXT iteration's GEMM1
+// (G1') picks them up.  GEMM1 has its own accumulator R, so it trails the epilogue by one chunk
+// instead of waiting for it to finish; the G accumulator and the slot are single-buffered, which
+// costs nothing because a chunk's epilogue (~1000 cycles) outlasts its MMAs (~500).
+// TMEM columns: y 256 | S 64 | r pieces 64 | R 64 | G 64 = 512.
 // kHist: 0 no stop-test record, 1 hist[it] += sum |z+ - z| (ista.py:93), 2 hist[it] += 1 if any
 // z+ != z (all a threshold of exactly 0 needs; cheaper than the sum)
 template <int NQ, int kHist>
 __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_w, bar_aready[2], bar_sfree[2], bar_rfull, bar_rready, bar_gfull[2], bar_gfree[2], bar_g2done;
+  __shared__ uint64_t bar_w, bar_aready, bar_sfree, bar_rfull, bar_rready, bar_gfull, bar_gfree;
   __shared__ uint32_t tmem_base_s;
 
-  constexpr uint32_t kUsesA = NQ >= 3 ? 2 : 1;                   // uses per iteration of slot S_A (q0, q2)
-  constexpr uint32_t kUsesB = NQ == 4 ? 2 : (NQ >= 2 ? 1 : 0);   // ... of slot S_B (q1, q3)
-  constexpr uint32_t kG0 = (NQ + 1) / 2, kG1 = NQ / 2;           // chunks per iteration in G buffer 0 / 1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int iters = p.iters;
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_aready[b], 512);
-      mbar_init(&bar_sfree[b], 1);
-      mbar_init(&bar_gfull[b], 1);
-      mbar_init(&bar_gfree[b], 512);
-    }
+    mbar_init(&bar_aready, 512);
+    mbar_init(&bar_sfree, 1);
+    mbar_init(&bar_gfull, 1);
+    mbar_init(&bar_gfree, 512);
     mbar_init(&bar_rfull, 1);
     mbar_init(&bar_rready, 512);
-    mbar_init(&bar_g2done, 1);
     fence_mbar_init();
   }
   if (warp == 16) {
@@ -219,57 +211,53 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     const uint32_t d2_lo = (uint32_t)desc2, d2_hi = (uint32_t)(desc2 >> 32);
     constexpr uint32_t kPiece16 = kPieceBytes >> 4;
     auto make64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    int tr_n = 0;
+    bool tr_on = false;
+    // slice q of GEMM1 of iteration `tg`: R (+)= Y[:, 64 q ...] W^T, three products per k-step
+    // into ONE accumulator (small ones first)
+    auto gemm1_slice = [&](int q, uint32_t tg) {
+      RES_WAIT(&bar_aready, tg * (uint32_t)NQ + (uint32_t)q);
+      RTRACE(11);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t t_slot = tbase + kColStage;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t koff = (uint32_t)q * (kSlabBytes >> 4) + (uint32_t)(ks * 2);
+          const uint64_t qh = make64(d1_lo + koff, d1_hi);
+          const uint64_t ql = make64(d1_lo + koff + kPiece16, d1_hi);
+          const uint32_t ah = t_slot + ks * 8, al = ah + 32;
+          mma_ts<false>(tbase + kColAccR, ah, ql, idesc1, (q > 0 || ks > 0) ? 1u : 0u);
+          mma_ts<false>(tbase + kColAccR, al, qh, idesc1, 1);
+          mma_ts<false>(tbase + kColAccR, ah, qh, idesc1, 1);
+        }
+        if (q == NQ - 1) mma_commit(&bar_rfull);
+        else mma_commit(&bar_sfree);
+      }
+      __syncwarp();
+      RTRACE(12);
+    };
     RES_WAIT(&bar_w, 0);
     uint32_t gi = 0;                   // global iteration counter (over tiles)
-    int tr_n = 0;
     for (int tile = 0; tile < my_tiles; ++tile) {
+      // GEMM1 of the tile's first iteration, from the pieces of y_0
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) gemm1_slice(q, gi);
       for (int it = 0; it < iters; ++it, ++gi) {
-        const bool tr_on = blockIdx.x == 0 && tile == 0 && (it == 3 || it == 4);
-        // ---- GEMM1: accumulators alias the G buffers: both must have been drained ----
+        tr_on = blockIdx.x == 0 && tile == 0 && (it == 3 || it == 4);
+        const bool more = it + 1 < iters;
         RTRACE(18);
-        if (gi > 0) {
-          RES_WAIT(&bar_gfree[0], gi * kG0 - 1u);
-          if (kG1 > 0) RES_WAIT(&bar_gfree[1], gi * kG1 - 1u);
-        }
-        RTRACE(10);
-        tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int s = q & 1;
-          RES_WAIT(&bar_aready[s], gi * (s ? kUsesB : kUsesA) + (uint32_t)(q >> 1));
-          RTRACE(11);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t t_slot = tbase + (s ? kColR : kColStage);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t koff = (uint32_t)q * (kSlabBytes >> 4) + (uint32_t)(ks * 2);
-              const uint32_t acc_on = (q > 0 || ks > 0) ? 1u : 0u;
-              const uint64_t qh = make64(d1_lo + koff, d1_hi);
-              const uint64_t ql = make64(d1_lo + koff + kPiece16, d1_hi);
-              const uint32_t ah = t_slot + ks * 8, al = ah + 32;
-              mma_ts<false>(tbase + kColAcc1, ah, ql, idesc1, acc_on);   // small products
-              mma_ts<false>(tbase + kColAcc1, al, qh, idesc1, 1);
-              mma_ts<false>(tbase + kColAcc0, ah, qh, idesc1, acc_on);   // leading product
-            }
-            if (q == NQ - 1) mma_commit(&bar_rfull);
-            else if (q + 2 < NQ) mma_commit(&bar_sfree[s]);   // the slot is written again this iteration
-          }
-          __syncwarp();
-          RTRACE(12);
-        }
-        // ---- GEMM2 ----
         RES_WAIT(&bar_rready, gi);
         RTRACE(14);
         tc_fence_after();
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          const int b = q & 1;
-          if (q >= 2) RES_WAIT(&bar_gfree[b], gi * (b ? kG1 : kG0) + (uint32_t)(q >> 1) - 1u);
+          // ---- GEMM2 chunk q: G = r W[:, 64 q ...]; the single G buffer must have been drained ----
+          if (q >= 1) RES_WAIT(&bar_gfree, gi * (uint32_t)NQ + (uint32_t)q - 1u);
           RTRACE(15);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t t_acc = tbase + (b ? kColAcc1 : kColAcc0);
+            const uint32_t t_acc = tbase + kColAccG;
             const uint32_t t_r = tbase + kColR;
             const uint32_t qoff = (uint32_t)q * (kSlabBytes >> 4);
             uint32_t acc_on = 0;
@@ -286,12 +274,14 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
                 }
               }
             }
-            mma_commit(&bar_gfull[b]);
-            if (q == NQ - 1) mma_commit(&bar_g2done);
+            mma_commit(&bar_gfull);
           }
           __syncwarp();
           RTRACE(16);
+          // ---- GEMM1 of the next iteration trails the epilogue by one chunk ----
+          if (more && q >= 1) gemm1_slice(q - 1, gi + 1);
         }
+        if (more) gemm1_slice(NQ - 1, gi + 1);
       }
     }
   } else {
@@ -312,21 +302,25 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     bool bad = false;
     uint32_t gi = 0;
 
-    // 16 values -> fp16 pieces (8 + 8 packed words)
-    auto split16 = [&](const uint32_t (&yv)[16], uint32_t (&wh)[8], uint32_t (&wl)[8]) {
+    // 16 values -> fp16 pieces -> this thread's 8 + 8 words of the slot [h 32 cols][l 32 cols];
+    // chunk q of the GEMM1 of iteration `tg`
+    auto stage_pieces = [&](const uint32_t (&yv)[16], int q, uint32_t tg) {
+      uint32_t wh[8], wl[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         split2_pair(make_float2(__uint_as_float(yv[2 * j]), __uint_as_float(yv[2 * j + 1])), wh[j], wl[j]);
-    };
-    // pieces -> slot s (0: S_A, 1: S_B): [h 32 cols][l 32 cols], this thread's 8 + 8 words
-    auto store_pieces = [&](int s, const uint32_t (&wh)[8], const uint32_t (&wl)[8]) {
-      const uint32_t t_slot = tbase + lane_base + (s ? kColR : kColStage) + wg * 8;
+      RTRACE(21);
+      // the slot is free once slice q - 1 has been consumed (q = 0: GEMM1 of the previous
+      // iteration is complete, everybody saw bar_rfull)
+      if (q >= 1) RES_WAIT(&bar_sfree, tg * (uint32_t)(NQ - 1) + (uint32_t)q - 1u);
+      RTRACE(22);
+      const uint32_t t_slot = tbase + lane_base + kColStage + wg * 8;
       tc_fence_after();
       tmem_st8(t_slot, wh);
       tmem_st8(t_slot + 32, wl);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bar_aready[s]);
+      mbar_arrive(&bar_aready);
       RTRACE(23);
     };
 
@@ -359,7 +353,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       // ---------------- y_0 = z_0 (ista.py:76) and its pieces ----------------
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        uint32_t yv[16], wh[8], wl[8];
+        uint32_t yv[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 z4 = *reinterpret_cast<const float4*>(zs + z_off(row, q * 16 + wg * 4 + j));
@@ -369,9 +363,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           yv[4 * j + 3] = __float_as_uint(z4.w);
         }
         tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
-        split16(yv, wh, wl);
-        if (q >= 2) RES_WAIT(&bar_sfree[q & 1], gi);   // second use of the slot
-        store_pieces(q & 1, wh, wl);
+        stage_pieces(yv, q, gi);
       }
 
       for (int it = 0; it < iters; ++it) {
@@ -387,18 +379,15 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           RES_WAIT(&bar_rfull, gi);
           RTRACE(30);
           tc_fence_after();
-          uint32_t rb[16], rs[16];
-          tmem_ld16(tbase + lane_base + kColAcc0 + wg * 16, rb);
-          tmem_ld16(tbase + lane_base + kColAcc1 + wg * 16, rs);
+          uint32_t rr[16];
+          tmem_ld16(tbase + lane_base + kColAccR + wg * 16, rr);
           tmem_wait_ld();
           uint32_t wh[8], wl[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 ra = rsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 0]), __uint_as_float(rb[4 * j + 1])),
-                                               make_float2(__uint_as_float(rs[4 * j + 0]), __uint_as_float(rs[4 * j + 1]))),
+            const float2 ra = rsub2(make_float2(__uint_as_float(rr[4 * j + 0]), __uint_as_float(rr[4 * j + 1])),
                                     make_float2(xv[j].x, xv[j].y));
-            const float2 rc = rsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3])),
-                                               make_float2(__uint_as_float(rs[4 * j + 2]), __uint_as_float(rs[4 * j + 3]))),
+            const float2 rc = rsub2(make_float2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])),
                                     make_float2(xv[j].z, xv[j].w));
             split2_pair(ra, wh[2 * j], wl[2 * j]);
             split2_pair(rc, wh[2 * j + 1], wl[2 * j + 1]);
@@ -414,20 +403,17 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         // ---------------- phase C (+ pieces of the next iteration) ----------------
         float part = 0.f;
         uint32_t any = 0;
-        const uint32_t tgt = gi + 1;           // iteration that consumes the pieces made now
-        uint32_t hh[8], hl[8];                 // pieces of q2, parked until slot S_A is free again
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          const int b = q & 1;
-          RES_WAIT(&bar_gfull[b], gi * (b ? kG1 : kG0) + (uint32_t)(q >> 1));
+          RES_WAIT(&bar_gfull, gi * (uint32_t)NQ + (uint32_t)q);
           RTRACE(40);
           tc_fence_after();
           uint32_t g[16], yv[16];
-          tmem_ld16(tbase + lane_base + (b ? kColAcc1 : kColAcc0) + wg * 16, g);
+          tmem_ld16(tbase + lane_base + kColAccG + wg * 16, g);
           tmem_ld16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
           tmem_wait_ld();
           tc_fence_before();
-          mbar_arrive(&bar_gfree[b]);   // accumulator is in registers: hand the buffer back
+          mbar_arrive(&bar_gfree);   // accumulator is in registers: hand the buffer back
           RTRACE(42);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -456,25 +442,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           }
           tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
           RTRACE(41);
-          if (!more) {
-            tmem_wait_st();
-          } else if (q == 2 && NQ == 4) {
-            split16(yv, hh, hl);          // S_A is busy until GEMM1 starts, i.e. after C(3)'s g-load
-            tmem_wait_st();
-          } else {
-            uint32_t wh[8], wl[8];
-            split16(yv, wh, wl);
-            RTRACE(21);
-            if (q == 1) RES_WAIT(&bar_g2done, gi);       // S_B aliases the r pieces of this iteration
-            if (q == 2) RES_WAIT(&bar_sfree[0], tgt);    // (NQ = 3) second use of S_A
-            if (q == 3) {
-              RES_WAIT(&bar_sfree[0], tgt);
-              store_pieces(0, hh, hl);
-              RES_WAIT(&bar_sfree[1], tgt);
-            }
-            RTRACE(22);
-            store_pieces(q & 1, wh, wl);   // its wait::st also covers the y store
-          }
+          if (more) stage_pieces(yv, q, gi + 1);   // its wait::st also covers the y store
+          else tmem_wait_st();
         }
         if (kHist == 1) {
           float s = part;
