@@ -36,6 +36,12 @@ struct Workspace {
 };
 constexpr int kMaxDevices = 64;
 Workspace g_ws[kMaxDevices];
+// copy streams / events of the host entry point's pipeline
+struct HostPipe {
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> events;
+};
+HostPipe g_pipe[kMaxDevices];
 std::mutex g_ws_mutex;
 
 int ensure(Buffer& b, size_t bytes) {
@@ -154,6 +160,10 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
     set_error("invalid maxiter=%d / lr=%g / alpha=%g", maxiter, lr, alpha);
     return LASSO_B200_ERR_INVALID;
   }
+  if (n == 0) {
+    if (iters_done) *iters_done = 0;
+    return LASSO_B200_OK;
+  }
   if (path == LASSO_B200_PATH_AUTO) path = lasso_b200_select_path(n, d, k);
   if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05 &&
       path != LASSO_B200_PATH_RESIDENT) {
@@ -168,10 +178,6 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   cudaStream_t st = (cudaStream_t)stream;
   const size_t code_bytes = sizeof(float) * (size_t)n * (size_t)k;
 
-  if (n == 0) {
-    if (iters_done) *iters_done = 0;
-    return LASSO_B200_OK;
-  }
   if (maxiter == 0) {
     if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_out, 0, code_bytes, st));
     else if (z0 != z_out)
@@ -319,28 +325,108 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
     if (delta_hist) dh = (double*)((char*)ws->hz.ptr + ((zb + 7) & ~(size_t)7));
   }
   cudaStream_t st = nullptr;  // legacy default stream: ordered with the copies below
-  LASSO_CUDA_TRY(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, st));
-  LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
-  if (z0) LASSO_CUDA_TRY(cudaMemcpyAsync(dz, z0, zb, cudaMemcpyHostToDevice, st));
-  rc = lasso_b200_fista_f32(dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, maxiter, fast,
-                            tol_abs, nullptr, dh, path, st);
-  if (rc) return rc;
-  LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, dz, zb, cudaMemcpyDeviceToHost, st));
-  if (delta_hist && maxiter > 0)
-    LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, dh, sizeof(double) * (size_t)maxiter,
-                                   cudaMemcpyDeviceToHost, st));
-  LASSO_CUDA_TRY(cudaStreamSynchronize(st));
-  if (iters_done) {
-    // recompute on the host from the history when it was requested, else re-run the scan
-    int done = maxiter;
-    if (tol_abs >= 0.0 && maxiter > 0) {
+  int done = maxiter;
+
+  // Resident kernel: the batch is cut into waves (one tile per SM) that flow through a
+  // three-stage pipeline -- H2D of x on one copy stream, the solve on the compute stream, D2H of
+  // the codes on a second copy stream -- so that all but the first upload and the last download
+  // hide behind the kernels.  A stop test that fired early, or a hand-over to the streaming
+  // kernel, falls through to the plain copy-solve-copy sequence below (z0 is re-read from the host).
+  const int resolved = path == LASSO_B200_PATH_AUTO ? lasso_b200_select_path(n, d, k) : path;
+  bool finished = false, replay = false;
+  if (resolved == LASSO_B200_PATH_RESIDENT && fista_res_supported(n, d, k) && maxiter > 0 &&
+      std::isfinite(lr) && lr > 0.0 && std::isfinite(alpha)) {
+    int dev = 0;
+    LASSO_CUDA_TRY(cudaGetDevice(&dev));
+    HostPipe& hp = g_pipe[dev];
+    if (!hp.s_in) {
+      LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+      LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    }
+    double* hist = nullptr;
+    {
       std::lock_guard<std::mutex> lock(g_ws_mutex);
       Workspace* ws = nullptr;
       if ((rc = current_workspace(&ws))) return rc;
-      LASSO_CUDA_TRY(cudaMemcpy(&done, ws->ctl.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+      if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
+      hist = (double*)ws->hist.ptr;
     }
-    *iters_done = done;
+    const bool need_hist = tol_abs >= 0.0 || delta_hist != nullptr;
+    const int hist_mode = !need_hist ? 0 : ((delta_hist == nullptr && tol_abs == 0.0) ? 2 : 1);
+    const int64_t wave = fista_res_wave_rows(n);
+    const int64_t nchunks = (n + wave - 1) / wave;
+    while ((int64_t)hp.events.size() < 2 * nchunks) {
+      cudaEvent_t ev;
+      LASSO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      hp.events.push_back(ev);
+    }
+    LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
+    if ((rc = fista_res_prepare(dw, d, k, (float)lr, (float)(alpha * lr), maxiter, fast ? 1 : 0, st))) return rc;
+    if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+    // the copy streams must not run ahead of work of an earlier call still queued on `st`
+    LASSO_CUDA_TRY(cudaEventRecord(hp.events[0], st));
+    LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.events[0], 0));
+    LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.events[0], 0));
+    for (int64_t c = 0; c < nchunks; ++c) {
+      const int64_t r0 = c * wave, rows = std::min<int64_t>(wave, n - r0);
+      LASSO_CUDA_TRY(cudaMemcpyAsync(dx + r0 * d, x + r0 * d, sizeof(float) * (size_t)rows * d,
+                                     cudaMemcpyHostToDevice, hp.s_in));
+      if (z0)
+        LASSO_CUDA_TRY(cudaMemcpyAsync(dz + r0 * k, z0 + r0 * k, sizeof(float) * (size_t)rows * k,
+                                       cudaMemcpyHostToDevice, hp.s_in));
+      LASSO_CUDA_TRY(cudaEventRecord(hp.events[2 * c], hp.s_in));
+    }
+    for (int64_t c = 0; c < nchunks; ++c) {
+      const int64_t r0 = c * wave, rows = std::min<int64_t>(wave, n - r0);
+      LASSO_CUDA_TRY(cudaStreamWaitEvent(st, hp.events[2 * c], 0));
+      if ((rc = fista_res_launch(dx + r0 * d, z0 ? dz + r0 * k : nullptr, dz + r0 * k, rows, d, k, maxiter,
+                                 need_hist ? hist : nullptr, hist_mode, fista_res_tile_rows(n), st)))
+        return rc;
+      LASSO_CUDA_TRY(cudaEventRecord(hp.events[2 * c + 1], st));
+      LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.events[2 * c + 1], 0));
+      LASSO_CUDA_TRY(cudaMemcpyAsync(z_out + r0 * k, dz + r0 * k, sizeof(float) * (size_t)rows * k,
+                                     cudaMemcpyDeviceToHost, hp.s_out));
+    }
+    int fell_back = 0;
+    if ((rc = fista_res_finish(&fell_back, st))) return rc;
+    if (!fell_back && tol_abs >= 0.0 && maxiter > 1) {
+      std::vector<double> h((size_t)maxiter);
+      LASSO_CUDA_TRY(cudaMemcpy(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+      for (int i = 0; i + 1 < maxiter; ++i)
+        if (h[(size_t)i] <= tol_abs) {
+          done = i + 1;
+          replay = true;
+          break;
+        }
+    }
+    LASSO_CUDA_TRY(cudaStreamSynchronize(hp.s_out));
+    if (!fell_back && !replay) {
+      if (delta_hist)
+        LASSO_CUDA_TRY(cudaMemcpy(delta_hist, hist, sizeof(double) * (size_t)maxiter, cudaMemcpyDeviceToHost));
+      finished = true;
+    } else if (fell_back) {
+      g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
+      path = LASSO_B200_PATH_TCGEN05;
+    }
   }
+  if (!finished) {
+    LASSO_CUDA_TRY(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, st));
+    LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
+    if (z0) LASSO_CUDA_TRY(cudaMemcpyAsync(dz, z0, zb, cudaMemcpyHostToDevice, st));
+    if (dh && maxiter > 0) LASSO_CUDA_TRY(cudaMemsetAsync(dh, 0, sizeof(double) * (size_t)maxiter, st));
+    // replay of a run whose stop test fired at iteration `done`: exactly that many iterations
+    int inner_done = maxiter;
+    rc = lasso_b200_fista_f32(dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, replay ? done : maxiter,
+                              fast, replay ? -1.0 : tol_abs, &inner_done, dh, path, st);
+    if (rc) return rc;
+    if (!replay) done = inner_done;
+    LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, dz, zb, cudaMemcpyDeviceToHost, st));
+    if (delta_hist && maxiter > 0)
+      LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, dh, sizeof(double) * (size_t)maxiter,
+                                     cudaMemcpyDeviceToHost, st));
+    LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (iters_done) *iters_done = done;
   return LASSO_B200_OK;
 }
 

@@ -100,17 +100,22 @@ struct FistaArgs {
 
 // scale factors of the resident kernel (fista_res.cu): all powers of two
 struct ResScalars {
-  float sx;    // x' = sx x
-  float sw;    // W' = sw W
-  float sz;    // z' = sz z   (sz = sx / sw)
-  float uz;    // z  = uz z'
+  float sw;    // W' = sw W; row r of x is scaled by its own sx_r, its codes by sx_r / sw
+  float isw;   // 1 / sw
   float lr;    // lr / sw^2
-  float lam;   // lam sz
-  int bad;     // inputs not finite / scaled step not representable
+  float lam;   // lam / sw   (times sx_r per row)
+  int bad;     // dictionary not finite / scaled step not representable
 };
 
 int fista_ffma_run(const FistaArgs& a, float* z_out, cudaStream_t st);
 bool fista_res_supported(int64_t n, int d, int k);
+int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int iters, int fast,
+                      cudaStream_t st);
+int64_t fista_res_wave_rows(int64_t n);
+int64_t fista_res_tile_rows(int64_t n);
+int fista_res_launch(const float* x, const float* z0, float* z_out, int64_t n, int d, int k, int iters,
+                     double* hist, int hist_mode, int64_t tile_rows, cudaStream_t st);
+int fista_res_finish(int* fell_back, cudaStream_t st);
 int fista_res_run(const float* x, const float* w, const float* z0, float* z_out, int64_t n, int d,
                   int k, float lr, float lam, int iters, int fast, double* hist, int hist_mode,
                   int* fell_back, cudaStream_t st);

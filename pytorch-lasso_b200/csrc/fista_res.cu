@@ -9,11 +9,11 @@
 //   operands  fp32 -> two fp16 pieces  v = h + l  (h = rn16(v), l = rn16(v - h); |v - h - l| <=
 //             2^-22 |v|), three tcgen05.mma kind::f16 products per k-step (h h', h l', l h')
 //             instead of the six of the bf16x3 split.  fp16 has a narrow exponent range, so
-//             the problem is rescaled by powers of two first (max|x| -> [64,128), max|W| ->
-//             [8,16), codes by their ratio): exact, the iterates are bit-for-bit the scaled
-//             iterates of the unscaled problem, and the low pieces stay normal numbers.  An
-//             iterate that would overflow fp16 anyway raises a flag and the caller re-runs
-//             the batch with the streaming bf16x3 kernel.
+//             every row's problem is rescaled by powers of two first (max|x_r| -> [64,128),
+//             max|W| -> [8,16), codes by their ratio): exact, the iterates are bit-for-bit the
+//             scaled iterates of the unscaled problem, and the low pieces stay normal numbers.
+//             An iterate that would overflow fp16 anyway ends as inf / NaN, raises a flag at
+//             the final store and the caller re-runs the batch with the streaming bf16x3 kernel.
 //   state     z_i  : shared memory, 128 x 256 fp32, XOR-swizzled rows (128 KB)
 //             y_i  : TMEM columns [0,256) fp32 (the momentum point, ista.py:100)
 //             x    : shared memory 128 x 64 fp32 (32 KB);  dictionary pieces: 64 KB
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_aready, bar_sfree, bar_rfull, bar_rready, bar_gfull, bar_gfree;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float row_sx[kTileM];   // per-row power-of-two scale of x (see the file header)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -296,7 +297,6 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     uint8_t* xs = smem + kSmemX;
     const ResScalars sc = *p.scal;
     const float2 nlr2 = make_float2(-sc.lr, -sc.lr);
-    const float lam = sc.lam;
     int tr_n = 0;
     bool tr_on = false;
     bool bad = false;
@@ -328,28 +328,44 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       const int64_t row0 = (int64_t)(blockIdx.x + (int64_t)tile * gridDim.x) * p.trows;
       int valid = p.trows;
       if (row0 + valid > p.n) valid = (int)(p.n - row0);
-      // ---------------- load the tile: x and z0, rescaled ----------------
+      // ---------------- load the tile: x and z0, rescaled per row ----------------
+      // Row r is scaled by sx_r = 2^(6 - exponent(max |x_r|)) (max |x'_r| in [64, 128)); its codes
+      // then live in units of sx_r / sw.  A row's result depends on that row alone, so any row
+      // split of a batch gives the same bits.
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int idx = ct + i * 512, r = idx >> 4, c4 = idx & 15;
+        const int idx = ct + i * 512, r = idx >> 4, c4 = idx & 15;   // 16 consecutive lanes share a row
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < valid && c4 * 4 < p.d) {
-          v = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.d + c4 * 4));
-          v.x *= sc.sx; v.y *= sc.sx; v.z *= sc.sx; v.w *= sc.sx;
+        if (r < valid && c4 * 4 < p.d) v = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.d + c4 * 4));
+        float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        // a non-finite row keeps scale 1, turns into inf / NaN codes and is caught at the store
+        float sxr = 1.f;
+        if (m > 0.f && m < 3.0e38f) {
+          // 2^(6 - e), e = unbiased exponent of m: biased exponent 127 + 6 - (E - 127)
+          const int be = 260 - (int)((__float_as_uint(m) >> 23) & 0xFFu);
+          sxr = __uint_as_float((uint32_t)min(max(be, 1), 254) << 23);
         }
+        v.x *= sxr; v.y *= sxr; v.z *= sxr; v.w *= sxr;
         *reinterpret_cast<float4*>(xs + x_off(r, c4)) = v;
+        if (c4 == 0) row_sx[r] = sxr;
       }
+      compute_sync();
 #pragma unroll 4
       for (int i = 0; i < 16; ++i) {
         const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.z0 != nullptr && r < valid && c4 * 4 < p.k) {
           v = __ldg(reinterpret_cast<const float4*>(p.z0 + (row0 + r) * p.k + c4 * 4));
-          v.x *= sc.sz; v.y *= sc.sz; v.z *= sc.sz; v.w *= sc.sz;
+          const float szr = row_sx[r] * sc.isw;
+          v.x *= szr; v.y *= szr; v.z *= szr; v.w *= szr;
         }
         *reinterpret_cast<float4*>(zs + z_off(r, c4)) = v;
       }
       compute_sync();
+      const float lam = sc.lam * row_sx[row];           // lam sx_r / sw
+      const float uz_row = sc.sw / row_sx[row];         // code units -> caller units (exact)
       // ---------------- y_0 = z_0 (ista.py:76) and its pieces ----------------
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
@@ -446,10 +462,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           else tmem_wait_st();
         }
         if (kHist == 1) {
-          float s = part;
+          float s = part * uz_row;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) atomicAdd(p.hist + it, (double)s * (double)sc.uz);
+          if (lane == 0) atomicAdd(p.hist + it, (double)s);
         }
         if (kHist == 2) {
           const bool moved = __any_sync(0xffffffffu, (any & 0x7FFFFFFFu) != 0u);
@@ -466,7 +482,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           float4 v = *reinterpret_cast<const float4*>(zs + z_off(r, c4));
           // an operand beyond the fp16 range turned into inf / NaN and stays that way
           bad |= !(fabsf(v.x) < p.limit) || !(fabsf(v.y) < p.limit) || !(fabsf(v.z) < p.limit) || !(fabsf(v.w) < p.limit);
-          v.x *= sc.uz; v.y *= sc.uz; v.z *= sc.uz; v.w *= sc.uz;
+          const float uzr = sc.sw / row_sx[r];
+          v.x *= uzr; v.y *= uzr; v.z *= uzr; v.w *= uzr;
           *reinterpret_cast<float4*>(p.z_out + (row0 + r) * p.k + c4 * 4) = v;
         }
       }
@@ -480,42 +497,28 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 }
 
 // ---- set-up kernels ---------------------------------------------------------------------
-// max |x|, max |W| as float bit patterns (non-negative floats order like unsigned ints);
-// a NaN / inf anywhere ends up as a huge pattern and is caught by res_setup_kernel
-__global__ void res_amax_kernel(const float* __restrict__ x, int64_t nx, const float* __restrict__ w, int nw,
-                                unsigned* __restrict__ out) {
-  unsigned m = 0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += stride)
-    m = max(m, __float_as_uint(x[i]) & 0x7FFFFFFFu);
-  m = __reduce_max_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out + 0, m);
-  if (blockIdx.x == 0) {
-    unsigned mw = 0;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) mw = max(mw, __float_as_uint(w[i]) & 0x7FFFFFFFu);
-    mw = __reduce_max_sync(0xffffffffu, mw);
-    if ((threadIdx.x & 31) == 0 && mw) atomicMax(out + 1, mw);
-  }
-}
-
-// scale factors (powers of two), scaled step / threshold, momentum table, flag reset
-__global__ void res_setup_kernel(const unsigned* __restrict__ amax, float lr, float lam, int iters, int fast,
+// scale of the dictionary (power of two, max |W'| in [8, 16)), scaled step / threshold, momentum
+// table, flag reset.  One block.
+__global__ void res_setup_kernel(const float* __restrict__ w, int nw, float lr, float lam, int iters, int fast,
                                  ResScalars* __restrict__ sc, float* __restrict__ beta, int* __restrict__ flag) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const float ax = __uint_as_float(amax[0]), aw = __uint_as_float(amax[1]);
-  int bad = 0;
-  int ex = 0, ew = 0;
-  if (!(ax < 3.0e38f) || !(aw < 3.0e38f)) bad = 1;
-  if (ax > 0.f && !bad) ex = 6 - ilogbf(ax);    // max |x'| in [64, 128)
-  if (aw > 0.f && !bad) ew = 3 - ilogbf(aw);    // max |W'| in [8, 16)
-  ex = max(-100, min(100, ex));
+  __shared__ unsigned s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  unsigned mw = 0;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) mw = max(mw, __float_as_uint(w[i]) & 0x7FFFFFFFu);
+  mw = __reduce_max_sync(0xffffffffu, mw);
+  if ((threadIdx.x & 31) == 0 && mw) atomicMax(&s_max, mw);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const float aw = __uint_as_float(s_max);   // NaN / inf have the largest bit patterns
+  int bad = 0, ew = 0;
+  if (!(aw < 3.0e38f)) bad = 1;
+  if (aw > 0.f && !bad) ew = 3 - ilogbf(aw);
   ew = max(-40, min(40, ew));
-  sc->sx = ldexpf(1.f, ex);
   sc->sw = ldexpf(1.f, ew);
-  sc->sz = ldexpf(1.f, ex - ew);
-  sc->uz = ldexpf(1.f, ew - ex);
+  sc->isw = ldexpf(1.f, -ew);
   sc->lr = ldexpf(lr, -2 * ew);
-  sc->lam = ldexpf(lam, ex - ew);
+  sc->lam = ldexpf(lam, -ew);
   if (!(sc->lr > 0.f) || !(sc->lr < 3.0e38f) || !(sc->lam < 3.0e38f) || (lam > 0.f && !(sc->lam > 0.f))) bad = 1;
   sc->bad = bad;
   *flag = bad;
@@ -546,7 +549,6 @@ __global__ void res_prep_w_kernel(const float* __restrict__ w, int d, int k, con
 struct ResState {
   uint8_t* w_image = nullptr;
   ResScalars* scal = nullptr;
-  unsigned* amax = nullptr;
   int* flag = nullptr;
   float* beta = nullptr;
   int beta_cap = 0;
@@ -565,21 +567,15 @@ bool fista_res_supported(int64_t n, int d, int k) {
          n < (int64_t)1 << 31;
 }
 
-// Runs `iters` iterations from z0 (nullptr = zeros) into z_out.  hist_mode: 0 none, 1 hist[it] =
-// sum |z_it - z_it+1|, 2 hist[it] > 0 iff z_it+1 != z_it (enough for a threshold of exactly 0).  *fell_back = 1 when an operand
-// left the fp16 range (z_out is then unspecified and the caller must use another path).
-// Synchronises the stream once (to read that flag).
-int fista_res_run(const float* x, const float* w, const float* z0, float* z_out, int64_t n, int d, int k,
-                  float lr, float lam, int iters, int fast, double* hist, int hist_mode, int* fell_back,
-                  cudaStream_t st) {
-  if (hist == nullptr) hist_mode = 0;
+// ---- host side: prepare (dictionary image, scalars, momentum table) / launch (a row range) /
+// finish (read the hand-over flag; the only synchronisation) -------------------------------------
+int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int iters, int fast, cudaStream_t st) {
   int dev = 0;
   LASSO_CUDA_TRY(cudaGetDevice(&dev));
   ResState& S = g_res[dev];
   if (!S.w_image) {
     LASSO_CUDA_TRY(cudaMalloc(&S.w_image, kWBytes));
     LASSO_CUDA_TRY(cudaMalloc(&S.scal, sizeof(ResScalars)));
-    LASSO_CUDA_TRY(cudaMalloc(&S.amax, 2 * sizeof(unsigned)));
     LASSO_CUDA_TRY(cudaMalloc(&S.flag, sizeof(int)));
     LASSO_CUDA_TRY(cudaDeviceGetAttribute(&S.num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
@@ -609,28 +605,49 @@ int fista_res_run(const float* x, const float* w, const float* z0, float* z_out,
       LASSO_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesR));
     S.attr_set = true;
   }
-  LASSO_CUDA_TRY(cudaMemsetAsync(S.amax, 0, 2 * sizeof(unsigned), st));
-  {
-    const int64_t nx = n * d;
-    int blocks = (int)((nx + 256 * 16 - 1) / (256 * 16));
-    if (blocks > S.num_sms * 8) blocks = S.num_sms * 8;
-    if (blocks < 1) blocks = 1;
-    res_amax_kernel<<<blocks, 256, 0, st>>>(x, nx, w, d * k, S.amax);
-    LASSO_CHECK_LAUNCH();
-    res_setup_kernel<<<1, 32, 0, st>>>(S.amax, lr, lam, iters, fast, S.scal, S.beta, S.flag);
-    LASSO_CHECK_LAUNCH();
-    res_prep_w_kernel<<<(kDP * kKP + 255) / 256, 256, 0, st>>>(w, d, k, S.scal, S.w_image);
-    LASSO_CHECK_LAUNCH();
-    count_launch(3);
-  }
-  // tile height: smallest multiple of 8 rows that keeps the number of waves of 128-row tiles
-  const int64_t slots = S.num_sms;
+  res_setup_kernel<<<1, 256, 0, st>>>(w, d * k, lr, lam, iters, fast, S.scal, S.beta, S.flag);
+  LASSO_CHECK_LAUNCH();
+  res_prep_w_kernel<<<(kDP * kKP + 255) / 256, 256, 0, st>>>(w, d, k, S.scal, S.w_image);
+  LASSO_CHECK_LAUNCH();
+  count_launch(2);
+  return LASSO_B200_OK;
+}
+
+// rows per tile: smallest multiple of 8 that keeps the number of waves of 128-row tiles
+static int64_t res_tile_rows(int64_t n, int num_sms) {
+  const int64_t slots = num_sms;
   const int64_t waves = ((n + kTileM - 1) / kTileM + slots - 1) / slots;
   int64_t trows = (n + waves * slots - 1) / (waves * slots);
   trows = ((trows + 7) / 8) * 8;
-  if (trows > kTileM) trows = kTileM;
+  return trows > kTileM ? kTileM : trows;
+}
+
+// rows one wave of tiles covers (one tile per SM) when a batch of n rows is cut for the host
+// pipeline of lasso_b200_fista_f32_host
+int64_t fista_res_wave_rows(int64_t n) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return res_tile_rows(n, sms) * sms;
+}
+
+int64_t fista_res_tile_rows(int64_t n) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return res_tile_rows(n, sms);
+}
+
+// iterations on rows [0, n) of x / z0 / z_out (pointers to the first of these rows); hist is shared
+// by all launches of a solve.  tile_rows = 0 picks the tile height from n.  No synchronisation.
+int fista_res_launch(const float* x, const float* z0, float* z_out, int64_t n, int d, int k, int iters,
+                     double* hist, int hist_mode, int64_t tile_rows, cudaStream_t st) {
+  if (hist == nullptr) hist_mode = 0;
+  int dev = 0;
+  LASSO_CUDA_TRY(cudaGetDevice(&dev));
+  ResState& S = g_res[dev];
+  const int64_t trows = tile_rows > 0 ? tile_rows : res_tile_rows(n, S.num_sms);
   const int64_t ntiles = (n + trows - 1) / trows;
   const unsigned grid = (unsigned)(ntiles < S.num_sms ? ntiles : S.num_sms);
+  const char* trace_path = getenv("LASSO_B200_TRACE");
 
   ResParams p{};
   p.w_image = S.w_image;
@@ -666,6 +683,16 @@ int fista_res_run(const float* x, const float* w, const float* z0, float* z_out,
 #undef LASSO_RES_LAUNCH
   LASSO_CHECK_LAUNCH();
   count_launch();
+  return LASSO_B200_OK;
+}
+
+// *fell_back = 1 when an operand left the fp16 range in any launch since the last prepare (the
+// codes are then unspecified and the caller must use another path).  Synchronises the stream.
+int fista_res_finish(int* fell_back, cudaStream_t st) {
+  int dev = 0;
+  LASSO_CUDA_TRY(cudaGetDevice(&dev));
+  ResState& S = g_res[dev];
+  const char* trace_path = getenv("LASSO_B200_TRACE");
   int flag = 0;
   cudaError_t e = cudaMemcpyAsync(&flag, S.flag, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -690,6 +717,17 @@ int fista_res_run(const float* x, const float* w, const float* z0, float* z_out,
   }
   *fell_back = flag;
   return LASSO_B200_OK;
+}
+
+// Runs `iters` iterations from z0 (nullptr = zeros) into z_out.  hist_mode: 0 none, 1 hist[it] =
+// sum |z_it - z_it+1|, 2 hist[it] > 0 iff z_it+1 != z_it (enough for a threshold of exactly 0).
+int fista_res_run(const float* x, const float* w, const float* z0, float* z_out, int64_t n, int d, int k,
+                  float lr, float lam, int iters, int fast, double* hist, int hist_mode, int* fell_back,
+                  cudaStream_t st) {
+  int rc = fista_res_prepare(w, d, k, lr, lam, iters, fast, st);
+  if (rc) return rc;
+  if ((rc = fista_res_launch(x, z0, z_out, n, d, k, iters, hist, hist_mode, 0, st))) return rc;
+  return fista_res_finish(fell_back, st);
 }
 
 }  // namespace lasso

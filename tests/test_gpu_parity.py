@@ -16,7 +16,16 @@ from lasso_b200.testing import make_problem, rel_fro, support_mismatch
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-PATHS = ["ffma", "auto"]
+PATHS = ["ffma", "auto", "tcgen05"]   # auto = resident tcgen05 kernel where the shape fits
+
+
+def _tc_shape(d, k):
+    return d % 4 == 0 and k % 4 == 0 and 4 <= d <= 64 and 4 <= k <= 256
+
+
+def _skip_unless_supported(path, d, k):
+    if path in ("tcgen05", "resident") and not _tc_shape(d, k):
+        pytest.skip("the tcgen05 kernels do not take d={} k={} (auto routes it to FFMA)".format(d, k))
 
 
 @pytest.fixture(scope="module")
@@ -35,6 +44,7 @@ def run_case(g, dev, path, **extra):
 @pytest.mark.parametrize("name", SOLVER_CASES)
 def test_golden_solver_cases(dev, name, path):
     g = load_golden(name)
+    _skip_unless_supported(path, g["weight"].shape[0], g["weight"].shape[1])
     z = run_case(g, dev, path)
     assert z.shape == g["z"].shape and z.dtype == torch.float32 and z.is_cuda
     assert rel_fro(z, g["z"]) <= TOL, name
@@ -45,6 +55,7 @@ def test_golden_solver_cases(dev, name, path):
 @pytest.mark.parametrize("init", ["zero", "ridge", "transpose"])
 def test_sparse_encode_inits(dev, init, path):
     g = load_golden("encode_init_" + init)
+    _skip_unless_supported(path, g["weight"].shape[0], g["weight"].shape[1])
     z = sparse_encode(g["x"].to(dev), g["weight"].to(dev), alpha=g["alpha"], algorithm="ista",
                       init=init, lr=g["lr"], maxiter=int(g["maxiter"]), tol=g["tol"], path=path)
     assert rel_fro(z, g["z"]) <= TOL
@@ -68,7 +79,7 @@ def test_early_stop_count_and_history(dev, path):
 
 @pytest.mark.parametrize("path", PATHS)
 def test_host_entry_point_equals_device_entry_point(dev, path):
-    g = load_golden("ista_ragged")
+    g = load_golden("ista_ragged" if path == "ffma" else "ista_warmstart")
     zd = run_case(g, dev, path)
     zh = ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=True, lr=g["lr"],
               maxiter=int(g["maxiter"]), tol=g["tol"], path=path)
@@ -82,35 +93,37 @@ def test_host_entry_point_equals_device_entry_point(dev, path):
 
 @pytest.mark.parametrize("path", PATHS)
 def test_edge_cases(dev, path):
-    x, w = make_problem(33, 7, 19, seed=2)
+    # ragged shape for the FFMA kernel, the nearest shape the tcgen05 kernels take otherwise
+    d, k = (7, 19) if path == "ffma" else (8, 20)
+    x, w = make_problem(33, d, k, seed=2)
     xd, wd = x.to(dev), w.to(dev)
     lr = 1.0 / oracle.lipschitz_constant(w)
     # maxiter = 0 through the C ABI copies the start
-    z0 = torch.rand(33, 19, device=dev)
+    z0 = torch.rand(33, k, device=dev)
     z, done, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, 0, True, 0.0, path=path, want_iters=True)
     assert done == 0 and torch.equal(z, z0)
     z, _, _ = _cabi.fista_device(xd, wd, None, 0.1, lr, 0, True, 0.0, path=path)
     assert float(z.abs().max()) == 0.0
     # empty batch
     ze = sparse_encode(xd[:0], wd, alpha=0.1, lr=lr, maxiter=5, path=path)
-    assert ze.shape == (0, 19)
+    assert ze.shape == (0, k)
     # single row, single iteration, odd/even iteration counts land in the caller's buffer
     for iters in (1, 2, 3, 4):
-        want = oracle.ista(x[:1], torch.zeros(1, 19), w, alpha=0.1, lr=lr, maxiter=iters, tol=0.0)
+        want = oracle.ista(x[:1], torch.zeros(1, k), w, alpha=0.1, lr=lr, maxiter=iters, tol=0.0)
         got = sparse_encode(xd[:1], wd, alpha=0.1, lr=lr, maxiter=iters, tol=0.0, path=path)
         assert rel_fro(got, want) <= TOL
     # result written in place over the start buffer (z_out aliases z0)
-    z0 = torch.zeros(33, 19, device=dev)
+    z0 = torch.zeros(33, k, device=dev)
     out, _, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, 7, True, 0.0, path=path, out=z0)
-    want = oracle.ista(x, torch.zeros(33, 19), w, alpha=0.1, lr=lr, maxiter=7, tol=0.0)
+    want = oracle.ista(x, torch.zeros(33, k), w, alpha=0.1, lr=lr, maxiter=7, tol=0.0)
     assert out.data_ptr() == z0.data_ptr() and rel_fro(z0, want) <= TOL
     # all codes shrink to zero -> delta == 0 -> the stop test fires at the first iteration
     z, done, _ = _cabi.fista_device(xd, wd, None, 1e3, lr, 9, True, 0.0, path=path, want_iters=True)
     assert done == 1 and float(z.abs().max()) == 0.0
     # non-contiguous inputs are accepted
-    xt = torch.randn(7, 33, device=dev).T
+    xt = torch.randn(d, 33, device=dev).T
     z = sparse_encode(xt, wd, alpha=0.1, lr=lr, maxiter=3, tol=0.0, path=path)
-    want = oracle.ista(xt.cpu().contiguous(), torch.zeros(33, 19), w, alpha=0.1, lr=lr, maxiter=3,
+    want = oracle.ista(xt.cpu().contiguous(), torch.zeros(33, k), w, alpha=0.1, lr=lr, maxiter=3,
                        tol=0.0)
     assert rel_fro(z, want) <= TOL
 
@@ -128,6 +141,82 @@ def test_deterministic_and_shard_invariant(dev, path):
     for shards in (2, 8, 3):
         parts = [sparse_encode(part.contiguous(), wd, **kw) for part in xd.chunk(shards)]
         assert torch.equal(torch.cat(parts), full)
+
+
+def test_auto_takes_the_resident_kernel(dev):
+    assert _cabi.select_path(65536, 64, 256) == _cabi.PATH_RESIDENT
+    assert _cabi.select_path(128, 10, 50) == _cabi.PATH_FFMA        # d % 4 != 0
+    assert _cabi.select_path(1000, 128, 1024) == _cabi.PATH_FFMA    # C3: dictionary exceeds one SM
+
+
+def test_resident_rows_at_wildly_different_scales(dev):
+    # every row is its own lasso problem and is rescaled on its own: the relative error of EACH
+    # row stays at the float32 level although the batch spans 12 orders of magnitude
+    n, d, k, iters = 600, 64, 256, 60
+    x, w = make_problem(n, d, k, seed=5, kind="planted")
+    g = torch.Generator().manual_seed(11)
+    scale = 10.0 ** (12 * torch.rand(n, 1, generator=g) - 6)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    got = torch.empty(n, k)
+    want = torch.empty(n, k)
+    # alpha scales with the row (alpha is a scalar of the API: solve in groups of equal scale)
+    for lo in range(0, n, 100):
+        sl = slice(lo, lo + 100)
+        s = float(scale[lo])
+        xs = x[sl] * s
+        want[sl] = oracle.ista(xs, torch.zeros(100, k), w, alpha=0.1 * s, lr=lr, maxiter=iters, tol=0.0)
+        got[sl] = sparse_encode(xs.to(dev), w.to(dev), alpha=0.1 * s, lr=lr, maxiter=iters, tol=0.0,
+                                path="resident").cpu()
+    row_err = (got - want).double().norm(dim=1) / want.double().norm(dim=1).clamp_min(1e-300)
+    assert float(row_err.max()) <= TOL
+    # one batch that mixes the scales (a single alpha): still per-row accurate
+    xm = x * scale
+    wantm = oracle.ista(xm, torch.zeros(n, k), w, alpha=0.05, lr=lr, maxiter=iters, tol=0.0)
+    gotm = sparse_encode(xm.to(dev), w.to(dev), alpha=0.05, lr=lr, maxiter=iters, tol=0.0, path="resident").cpu()
+    live = wantm.double().norm(dim=1) > 0
+    row_err = (gotm - wantm).double().norm(dim=1)[live] / wantm.double().norm(dim=1)[live]
+    assert float(row_err.max()) <= TOL
+    assert float(gotm[~live].abs().max() if (~live).any() else 0.0) == 0.0
+    assert _cabi.resident_fallbacks() == 0
+
+
+def test_resident_falls_back_to_the_streaming_kernel(dev, monkeypatch):
+    # LASSO_B200_RES_LIMIT lowers the operand bound at which the resident kernel gives up, so
+    # that the hand-over (flag, stream sync, streaming bf16x3 solve from the intact z0) is exercised
+    n, d, k = 300, 32, 128
+    x, w = make_problem(n, d, k, seed=6)
+    xd, wd = x.to(dev), w.to(dev)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    z0 = (0.05 * torch.randn(n, k)).to(dev)
+    before = _cabi.resident_fallbacks()
+    monkeypatch.setenv("LASSO_B200_RES_LIMIT", "1e-3")
+    buf = z0.clone()
+    got, done, _ = _cabi.fista_device(xd, wd, buf, 0.1, lr, 25, True, -1.0, path="resident",
+                                      want_iters=True, out=buf)      # z0 aliases the output
+    monkeypatch.delenv("LASSO_B200_RES_LIMIT")
+    assert _cabi.resident_fallbacks() == before + 1 and done == 25
+    stream, _, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, 25, True, -1.0, path="tcgen05")
+    assert torch.equal(got, stream)
+    # non-finite input: the resident kernel hands over as well instead of returning garbage silently
+    xb = xd.clone()
+    xb[3, 5] = float("inf")
+    got, _, _ = _cabi.fista_device(xb, wd, None, 0.1, lr, 5, True, -1.0, path="resident")
+    assert _cabi.resident_fallbacks() == before + 2
+    assert bool(torch.isfinite(got[:3]).all()) and bool(torch.isfinite(got[4:]).all())
+
+
+def test_resident_zero_threshold_stop_test(dev):
+    # tol = 0 keeps the reference's stop test armed: it fires when an iteration changes nothing
+    # (ista.py:93 with a threshold of 0).  The resident kernel records only "moved / did not move".
+    n, d, k = 200, 16, 64
+    x, w = make_problem(n, d, k, seed=7)
+    xd, wd = x.to(dev), w.to(dev)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    z, done, _ = _cabi.fista_device(xd, wd, None, 1e3, lr, 9, True, 0.0, path="resident", want_iters=True)
+    assert done == 1 and float(z.abs().max()) == 0.0
+    z, done, _ = _cabi.fista_device(xd, wd, None, 0.1, lr, 9, True, 0.0, path="resident", want_iters=True)
+    want = oracle.ista(x, torch.zeros(n, k), w, alpha=0.1, lr=lr, maxiter=9, tol=0.0)
+    assert done == 9 and rel_fro(z, want) <= TOL
 
 
 @pytest.mark.parametrize("kind", ["planted", "randn"])
