@@ -382,11 +382,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         stage_pieces(yv, q, gi);
       }
 
+      float beta_next = __ldg(p.beta);         // fetched one iteration ahead: a global load costs ~600 cycles
       for (int it = 0; it < iters; ++it) {
         tr_on = blockIdx.x == 0 && tile == 0 && (it == 3 || it == 4);
-        const float beta = __ldg(p.beta + it);
-        const float2 beta2 = make_float2(beta, beta);
         const bool more = it + 1 < iters;      // pieces are only needed if another GEMM1 follows
+        const float2 beta2 = make_float2(beta_next, beta_next);
+        if (more) beta_next = __ldg(p.beta + it + 1);
         // ---------------- phase B: r = R - x -> pieces (16 features per thread) ----------------
         {
           float4 xv[4];
