@@ -307,6 +307,109 @@ __global__ void __launch_bounds__(1024) dict_sweep_kernel(float* dict, double* g
   }
 }
 
+
+// Fast variant for dictionaries that fit shared memory (d * k floats <= 160 KB): the dictionary
+// lives in shared memory for the whole sweep, row j of A = Z^T Z is prefetched into registers one
+// atom ahead, every warp owns whole feature rows (no cross-warp reduction for D A_j), and one warp
+// forms the norm.  Two CTA barriers per atom instead of a dozen global round trips
+// (1.07 ms -> 0.90 ms for d = 64, k = 256; the sweep is a chain of 256 latency-bound steps).
+constexpr int kSweepMaxPerLane = 8;    // k <= 256 (row of A in registers: 8 doubles per lane)
+__global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, double* gzz, double* gzx, int d,
+                                                               int k, double eps,
+                                                               const float* __restrict__ redraw,
+                                                               int* __restrict__ zeroed) {
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  float* ds = reinterpret_cast<float*>(sweep_smem);                    // [d][k]
+  double* us = reinterpret_cast<double*>(sweep_smem + (size_t)d * k * sizeof(float));   // [d]
+  __shared__ double s_nrm;
+  __shared__ int s_deg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int e = tid; e < d * k; e += blockDim.x) ds[e] = dict[e];
+  double arow[kSweepMaxPerLane], anext[kSweepMaxPerLane];
+#pragma unroll
+  for (int m = 0; m < kSweepMaxPerLane; ++m) {
+    const int l = lane + 32 * m;
+    anext[m] = l < k ? gzz[l] : 0.0;                                    // row 0 of A
+  }
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+#pragma unroll
+    for (int m = 0; m < kSweepMaxPerLane; ++m) arow[m] = anext[m];
+    if (j + 1 < k) {
+#pragma unroll
+      for (int m = 0; m < kSweepMaxPerLane; ++m) {
+        const int l = lane + 32 * m;
+        if (l < k) anext[m] = gzz[(int64_t)(j + 1) * k + l];
+      }
+    }
+    const double ajj = gzz[(int64_t)j * k + j];
+    // u_i = B[j,i] - sum_l D[i,l] A[j,l] + A[j,j] D[i,j]
+    for (int i = warp; i < d; i += nwarps) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < kSweepMaxPerLane; ++m) {
+        const int l = lane + 32 * m;
+        if (l < k) s += (double)ds[i * k + l] * arow[m];
+      }
+      s = warp_sum(s);
+      if (lane == 0) us[i] = gzx[(int64_t)j * d + i] - s + ajj * (double)ds[i * k + j];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double part = 0.0;
+      for (int i = lane; i < d; i += 32) part += us[i] * us[i];
+      part = warp_sum(part);
+      if (lane == 0) {
+        const double nrm = sqrt(part);
+        s_nrm = nrm;
+        s_deg = nrm < eps ? 1 : 0;
+        zeroed[j] = s_deg;
+      }
+    }
+    __syncthreads();
+    double nrm = s_nrm;
+    if (s_deg) {
+      // the atom's codes are dropped (dict_learning.py:92-98): its row/column of the statistics
+      // vanish, so the replacement never influences the later atoms
+      for (int l = tid; l < k; l += blockDim.x) {
+        gzz[(int64_t)j * k + l] = 0.0;
+        gzz[(int64_t)l * k + j] = 0.0;
+      }
+      for (int i = tid; i < d; i += blockDim.x) gzx[(int64_t)j * d + i] = 0.0;
+      // the prefetched row j + 1 of A was read before its column j was cleared
+      if ((j & 31) == lane) {
+#pragma unroll
+        for (int m = 0; m < kSweepMaxPerLane; ++m)
+          if (m == (j >> 5)) anext[m] = 0.0;
+      }
+      nrm = 0.0;
+      if (redraw != nullptr) {
+        __syncthreads();
+        if (warp == 0) {
+          double part = 0.0;
+          for (int i = lane; i < d; i += 32) {
+            const double r = (double)redraw[(int64_t)i * k + j];
+            us[i] = r;
+            part += r * r;
+          }
+          part = warp_sum(part);
+          if (lane == 0) s_nrm = sqrt(part);
+        }
+        __syncthreads();
+        nrm = s_nrm;
+      }
+    }
+    if (nrm > 0.0) {
+      for (int i = tid; i < d; i += blockDim.x) {
+        const float v = (float)(us[i] / nrm);
+        ds[i * k + j] = v;
+        dict[(int64_t)i * k + j] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
@@ -341,6 +444,19 @@ int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gz
 
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
                     const float* redraw, int* zeroed, cudaStream_t st) {
+  const size_t smem = (size_t)d * k * sizeof(float) + (size_t)d * sizeof(double);
+  if (smem <= 160 * 1024 && k <= 32 * kSweepMaxPerLane) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_smem_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    dict_sweep_smem_kernel<<<1, 1024, smem, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+    return LASSO_B200_OK;
+  }
   double* u = nullptr;
   LASSO_CUDA_TRY(cudaMallocAsync(&u, sizeof(double) * (size_t)d, st));
   dict_sweep_kernel<<<1, 1024, 0, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed, u);
