@@ -44,6 +44,8 @@ constexpr int kDP = 64;            // padded d
 constexpr int kKP = 256;           // padded k
 constexpr int kThreadsR = 544;     // warps 0..15: compute, warp 16: MMA issuer (the SM's warp arbiter favours
                                    // high warp ids: as warp 0 the issuer starved behind the epilogue math)
+// (registers: the SM hands them out per 4 warps, so 17 warps are budgeted as 20 and 96 per thread is
+// the ceiling -- a 112-register build fails to launch)
 constexpr uint32_t kSlabBytes = kDP * 128;                 // [64 features][128 B] = 64 atoms of one piece
 constexpr uint32_t kPieceBytes = (kKP / 64) * kSlabBytes;  // 32 KB
 constexpr uint32_t kWBytes = 2 * kPieceBytes;              // 64 KB: h image, l image
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
   __shared__ uint64_t bar_w, bar_aready, bar_sfree, bar_rfull, bar_rready, bar_gfull, bar_gfree;
   __shared__ uint32_t tmem_base_s;
   __shared__ float row_sx[kTileM];   // per-row power-of-two scale of x (see the file header)
+  __shared__ float hist_s[2][16];    // per-warp stop-test records of the last two iterations
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int my_tiles = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -279,6 +282,14 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           }
           __syncwarp();
           RTRACE(16);
+          if (kHist != 0 && q == 0 && it > 0 && lane == 0) {
+            // stop-test record of the previous iteration: the compute warps left their partial
+            // sums in shared memory before they arrived on bar_rready; ONE atomic per CTA
+            double s = 0.0;
+#pragma unroll
+            for (int wi = 0; wi < 16; ++wi) s += (double)hist_s[(it - 1) & 1][wi];
+            if (kHist == 1 || s > 0.0) atomicAdd(p.hist + it - 1, s);
+          }
           // ---- GEMM1 of the next iteration trails the epilogue by one chunk ----
           if (more && q >= 1) gemm1_slice(q - 1, gi + 1);
         }
@@ -418,16 +429,17 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           RTRACE(31);
         }
         // ---------------- phase C (+ pieces of the next iteration) ----------------
-        float part = 0.f;
+        float part = 0.f, part_b = 0.f;   // two chains: 64 dependent adds per iteration otherwise
         uint32_t any = 0;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
+          // y does not depend on the MMAs: its load is in flight while this thread waits for G
+          uint32_t g[16], yv[16];
+          tmem_ld16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
           RES_WAIT(&bar_gfull, gi * (uint32_t)NQ + (uint32_t)q);
           RTRACE(40);
           tc_fence_after();
-          uint32_t g[16], yv[16];
           tmem_ld16(tbase + lane_base + kColAccG + wg * 16, g);
-          tmem_ld16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
           tmem_wait_ld();
           tc_fence_before();
           mbar_arrive(&bar_gfree);   // accumulator is in registers: hand the buffer back
@@ -448,7 +460,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
               const float2 c = make_float2(fminf(fmaxf(v.x, -lam), lam), fminf(fmaxf(v.y, -lam), lam));
               const float2 zn = rsub2(v, c);
               const float2 dl = rsub2(zn, zz);                       // z+ - z
-              if (kHist == 1) part += fabsf(dl.x) + fabsf(dl.y);     // stop-test sum (ista.py:93)
+              if (kHist == 1) {                                      // stop-test sum (ista.py:93)
+                if (h2) part_b += fabsf(dl.x) + fabsf(dl.y);
+                else part += fabsf(dl.x) + fabsf(dl.y);
+              }
               if (kHist == 2) any |= __float_as_uint(dl.x) | __float_as_uint(dl.y);
               const float2 yn = __ffma2_rn(beta2, dl, zn);           // ista.py:100
               zo[h2] = zn;
@@ -462,15 +477,21 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           if (more) stage_pieces(yv, q, gi + 1);   // its wait::st also covers the y store
           else tmem_wait_st();
         }
-        if (kHist == 1) {
-          float s = part * uz_row;
+        if (kHist != 0) {
+          float s;
+          if (kHist == 1) {
+            s = (part + part_b) * uz_row;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) atomicAdd(p.hist + it, (double)s);
-        }
-        if (kHist == 2) {
-          const bool moved = __any_sync(0xffffffffu, (any & 0x7FFFFFFFu) != 0u);
-          if (lane == 0 && moved) atomicAdd(p.hist + it, 1.0);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          } else {
+            s = __any_sync(0xffffffffu, (any & 0x7FFFFFFFu) != 0u) ? 1.f : 0.f;
+          }
+          if (lane == 0) {
+            // the MMA warp adds the 16 partial records up after the next bar_rready (one atomic
+            // per CTA and iteration); nobody comes after a tile's last iteration
+            if (more) hist_s[it & 1][warp] = s;
+            else if (kHist == 1 || s > 0.f) atomicAdd(p.hist + it, (double)s);
+          }
         }
         ++gi;
       }
