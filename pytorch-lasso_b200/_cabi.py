@@ -12,7 +12,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblasso_b200.so")
+# LASSO_B200_LIB: load another build of the library (kernel variants, tools/variants.sh)
+LIB_PATH = os.environ.get("LASSO_B200_LIB") or os.path.join(_HERE, "csrc", "liblasso_b200.so")
 
 PATH_AUTO, PATH_FFMA, PATH_TCGEN05, PATH_RESIDENT = 0, 1, 2, 3
 _PATH_NAMES = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tcgen05": PATH_TCGEN05,

@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(CSRC, "liblasso_b200.so")
+OUT = os.environ.get("LASSO_B200_LIB") or os.path.join(CSRC, "liblasso_b200.so")
 SOURCES = ["cabi.cu", "fista_ffma.cu", "fista_tc.cu", "fista_res.cu", "aux_kernels.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "lasso_b200.h")]
 NVCC_FLAGS = [
@@ -42,7 +42,7 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("LASSO_B200_EXTRA_FLAGS", "").split()
     if os.environ.get("LASSO_B200_BUILD_TRACE"):   # per-warp timeline instrumentation (tools/tc_trace.py)
         flags.append("-DLASSO_RES_TRACE")
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES

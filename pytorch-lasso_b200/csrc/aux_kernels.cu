@@ -1,5 +1,7 @@
 // Small kernels around the FISTA loop: Lipschitz constant (power iteration),
 // M-step sufficient statistics (Gram matrices) and the Gram-space atom sweep.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lasso {
@@ -308,67 +310,110 @@ __global__ void __launch_bounds__(1024) dict_sweep_kernel(float* dict, double* g
 }
 
 
-// Fast variant for dictionaries that fit shared memory (d * k floats <= 160 KB): the dictionary
-// lives in shared memory for the whole sweep, row j of A = Z^T Z is prefetched into registers one
-// atom ahead, every warp owns whole feature rows (no cross-warp reduction for D A_j), and one warp
-// forms the norm.  Two CTA barriers per atom instead of a dozen global round trips
-// (1.07 ms -> 0.90 ms for d = 64, k = 256; the sweep is a chain of 256 latency-bound steps).
-constexpr int kSweepMaxPerLane = 8;    // k <= 256 (row of A in registers: 8 doubles per lane)
+// Fast variant for dictionaries that fit shared memory (d * k floats <= 150 KB, k <= 256).
+//  * the dictionary lives in shared memory for the whole sweep; the rows of A = Z^T Z, B = Z^T X
+//    that step j needs are prefetched three steps ahead with cp.async (no global load on the
+//    critical path of the 256-step chain);
+//  * the diagonal term cancels analytically: u_i = B[j,i] - sum_{l != j} D[i,l] A[j,l], so the
+//    two large contributions A[j,j] D[i,j] never meet and the inner products can run in float32
+//    (as the reference's own update does, dict_learning.py:85-86) -- the float64 pipe of this GPU
+//    issues only a few operations per clock and was the bottleneck of the float64 version;
+//    u, its norm and the normalisation stay in float64;
+//  * rows/columns of dropped atoms are masked on read (the prefetched copies may predate their
+//    clearing in global memory).
+constexpr int kSweepMaxPerLane = 8;    // k <= 256
+constexpr int kSweepDepth = 4;         // row buffers
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
 __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, double* gzz, double* gzx, int d,
                                                                int k, double eps,
                                                                const float* __restrict__ redraw,
                                                                int* __restrict__ zeroed) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
-  float* ds = reinterpret_cast<float*>(sweep_smem);                    // [d][k]
-  double* us = reinterpret_cast<double*>(sweep_smem + (size_t)d * k * sizeof(float));   // [d]
-  __shared__ double s_nrm;
-  __shared__ int s_deg;
+  double* arow = reinterpret_cast<double*>(sweep_smem);                               // [depth][k]
+  double* brow = arow + kSweepDepth * k;                                              // [depth][d]
+  double* us = brow + kSweepDepth * d;                                                // [d]
+  float* ds = reinterpret_cast<float*>(us + d);                                       // [d][k]
+  float* af = ds + (size_t)d * k;                                                     // [k]
+  unsigned char* dead = reinterpret_cast<unsigned char*>(af + k);                     // [k]
+  __shared__ double s_inv, s_nrm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  for (int e = tid; e < d * k; e += blockDim.x) ds[e] = dict[e];
-  double arow[kSweepMaxPerLane], anext[kSweepMaxPerLane];
-#pragma unroll
-  for (int m = 0; m < kSweepMaxPerLane; ++m) {
-    const int l = lane + 32 * m;
-    anext[m] = l < k ? gzz[l] : 0.0;                                    // row 0 of A
-  }
-  __syncthreads();
-  for (int j = 0; j < k; ++j) {
-#pragma unroll
-    for (int m = 0; m < kSweepMaxPerLane; ++m) arow[m] = anext[m];
-    if (j + 1 < k) {
-#pragma unroll
-      for (int m = 0; m < kSweepMaxPerLane; ++m) {
-        const int l = lane + 32 * m;
-        if (l < k) anext[m] = gzz[(int64_t)(j + 1) * k + l];
-      }
+  const int a_chunks = k / 2, b_chunks = d / 2;   // 16-byte pieces of a row of A / B (k, d even)
+  auto prefetch = [&](int j) {
+    if (j < k) {
+      const int slot = j % kSweepDepth;
+      if (tid < a_chunks) cp_async16(arow + slot * k + tid * 2, gzz + (int64_t)j * k + tid * 2);
+      else if (tid < a_chunks + b_chunks)
+        cp_async16(brow + slot * d + (tid - a_chunks) * 2, gzx + (int64_t)j * d + (tid - a_chunks) * 2);
     }
-    const double ajj = gzz[(int64_t)j * k + j];
-    // u_i = B[j,i] - sum_l D[i,l] A[j,l] + A[j,j] D[i,j]
-    for (int i = warp; i < d; i += nwarps) {
-      double s = 0.0;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int e = tid; e < d * k; e += blockDim.x) ds[e] = dict[e];
+  for (int l = tid; l < k; l += blockDim.x) dead[l] = 0;
+  for (int j = 0; j < kSweepDepth - 1; ++j) prefetch(j);
+  for (int j = 0; j < k; ++j) {
+    prefetch(j + kSweepDepth - 1);                                   // into the slot step j - 1 released
+    asm volatile("cp.async.wait_group %0;" ::"n"(kSweepDepth - 1) : "memory");   // row j has landed
+    __syncthreads();
+    const double* aj = arow + (j % kSweepDepth) * k;
+    const double* bj = brow + (j % kSweepDepth) * d;
+    for (int l = tid; l < k; l += blockDim.x) af[l] = (l == j || dead[l]) ? 0.f : (float)aj[l];
+    __syncthreads();
+    // u_i = B[j,i] - sum_{l != j} D[i,l] A[j,l]; two rows per warp in flight
+    for (int i0 = warp; i0 < d; i0 += 2 * nwarps) {
+      const int i1 = i0 + nwarps;
+      const bool two = i1 < d;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int m = 0; m < kSweepMaxPerLane; ++m) {
         const int l = lane + 32 * m;
-        if (l < k) s += (double)ds[i * k + l] * arow[m];
+        if (l < k) {
+          const float a = af[l];
+          s0 = fmaf(ds[i0 * k + l], a, s0);
+          if (two) s1 = fmaf(ds[i1 * k + l], a, s1);
+        }
       }
-      s = warp_sum(s);
-      if (lane == 0) us[i] = gzx[(int64_t)j * d + i] - s + ajj * (double)ds[i * k + j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if (lane == 0) {
+        us[i0] = bj[i0] - (double)s0;
+        if (two) us[i1] = bj[i1] - (double)s1;
+      }
     }
     __syncthreads();
+    // one warp forms the norm (float64 is scarce on this GPU: 32 warps doing it redundantly cost
+    // more than a barrier).  1 / |u| comes from a float rsqrt refined by three Newton steps in
+    // float64 (full double accuracy); the library sqrt and divide are long software sequences
     if (warp == 0) {
       double part = 0.0;
       for (int i = lane; i < d; i += 32) part += us[i] * us[i];
-      part = warp_sum(part);
+      const double ss = warp_sum(part);
+      double inv = 0.0;
+      if (ss > 0.0 && ss < 1e300) {
+        if (ss < 1e-30 || ss > 1e30) {
+          inv = 1.0 / sqrt(ss);                             // out of float range: slow exact path
+        } else {
+          inv = (double)rsqrtf((float)ss);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) inv = inv * (1.5 - 0.5 * ss * inv * inv);
+        }
+      }
       if (lane == 0) {
-        const double nrm = sqrt(part);
-        s_nrm = nrm;
-        s_deg = nrm < eps ? 1 : 0;
-        zeroed[j] = s_deg;
+        s_inv = inv;
+        s_nrm = ss * inv;      // |u| (0 for an all-zero u)
       }
     }
     __syncthreads();
-    double nrm = s_nrm;
-    if (s_deg) {
+    double inv = s_inv, nrm = s_nrm, part;
+    const bool degenerate = nrm < eps;
+    if (tid == 0) zeroed[j] = degenerate ? 1 : 0;
+    if (degenerate) {
       // the atom's codes are dropped (dict_learning.py:92-98): its row/column of the statistics
       // vanish, so the replacement never influences the later atoms
       for (int l = tid; l < k; l += blockDim.x) {
@@ -376,32 +421,21 @@ __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, doub
         gzz[(int64_t)l * k + j] = 0.0;
       }
       for (int i = tid; i < d; i += blockDim.x) gzx[(int64_t)j * d + i] = 0.0;
-      // the prefetched row j + 1 of A was read before its column j was cleared
-      if ((j & 31) == lane) {
-#pragma unroll
-        for (int m = 0; m < kSweepMaxPerLane; ++m)
-          if (m == (j >> 5)) anext[m] = 0.0;
-      }
+      if (tid == 0) dead[j] = 1;
       nrm = 0.0;
       if (redraw != nullptr) {
         __syncthreads();
-        if (warp == 0) {
-          double part = 0.0;
-          for (int i = lane; i < d; i += 32) {
-            const double r = (double)redraw[(int64_t)i * k + j];
-            us[i] = r;
-            part += r * r;
-          }
-          part = warp_sum(part);
-          if (lane == 0) s_nrm = sqrt(part);
-        }
+        for (int i = tid; i < d; i += blockDim.x) us[i] = (double)redraw[(int64_t)i * k + j];
         __syncthreads();
-        nrm = s_nrm;
+        part = 0.0;
+        for (int i = lane; i < d; i += 32) part += us[i] * us[i];
+        nrm = sqrt(warp_sum(part));
+        inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
       }
     }
     if (nrm > 0.0) {
       for (int i = tid; i < d; i += blockDim.x) {
-        const float v = (float)(us[i] / nrm);
+        const float v = (float)(us[i] * inv);
         ds[i * k + j] = v;
         dict[(int64_t)i * k + j] = v;
       }
@@ -444,15 +478,19 @@ int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gz
 
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
                     const float* redraw, int* zeroed, cudaStream_t st) {
-  const size_t smem = (size_t)d * k * sizeof(float) + (size_t)d * sizeof(double);
-  if (smem <= 160 * 1024 && k <= 32 * kSweepMaxPerLane) {
+  const size_t smem = sizeof(double) * ((size_t)kSweepDepth * (k + d) + d) +
+                      sizeof(float) * ((size_t)d * k + k) + (size_t)k;
+  if (smem <= 200 * 1024 && k <= 32 * kSweepMaxPerLane && (k % 2) == 0 && (d % 2) == 0 && k / 2 + d / 2 <= 1024) {
     static bool attr_set = false;
     if (!attr_set) {
       LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_smem_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    dict_sweep_smem_kernel<<<1, 1024, smem, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed);
+    int threads = 1024;
+    if (const char* t = getenv("LASSO_B200_SWEEP_THREADS")) threads = atoi(t);
+    if (threads < 256 || threads > 1024 || (threads % 32) != 0 || k / 2 + d / 2 > threads) threads = 1024;
+    dict_sweep_smem_kernel<<<1, threads, smem, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed);
     LASSO_CHECK_LAUNCH();
     count_launch();
     return LASSO_B200_OK;

@@ -97,6 +97,9 @@ __device__ __noinline__ void res_wait_slow_path(uint64_t& t0, volatile int* dbg,
   }
   __trap();
 }
+#ifndef LASSO_RES_HINT
+#define LASSO_RES_HINT 20000   // suspend-time hint of the waits, ns (0 / 1000 / 20000 measure the same)
+#endif
 #define RES_WAIT(bar, parity)                                                             \
   do {                                                                                    \
     const uint32_t _addr = smem_u32(bar), _par = (parity) & 1u;                           \
@@ -108,7 +111,7 @@ __device__ __noinline__ void res_wait_slow_path(uint64_t& t0, volatile int* dbg,
           "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"                  \
           "selp.b32 %0, 1, 0, P;\n\t}\n"                                                   \
           : "=r"(_ok)                                                                     \
-          : "r"(_addr), "r"(_par), "r"(20000u)                                            \
+          : "r"(_addr), "r"(_par), "r"((unsigned)LASSO_RES_HINT)                          \
           : "memory");                                                                    \
       if (_ok) break;                                                                     \
       if ((++_n & 1023u) == 0) res_wait_slow_path(_t0, p.dbg, __LINE__, _par);            \
