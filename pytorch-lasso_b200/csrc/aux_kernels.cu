@@ -187,6 +187,11 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ z,
   const int bi = blockIdx.y / nbj, bj = blockIdx.y % nbj;
   const int a0 = bi * kGT;   // atom block
   const int c0 = bj * kGT;   // column block of [Z | X]
+  // Z^T Z is symmetric: among the full 64-atom blocks, those below the diagonal are mirrored from
+  // the ones above
+  const int nzb = k / kGT;
+  if (bj < bi && bi < nzb) return;
+  const bool mirror = bi < bj && bj < nzb;
   const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
   const int64_t r_begin = (int64_t)blockIdx.x * kGSlab;
   const int64_t r_end = min(n, r_begin + kGSlab);
@@ -215,6 +220,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ z,
 #pragma unroll 8
     for (int rr = 0; rr < kGR; ++rr) {
       const float4 a = *reinterpret_cast<const float4*>(&As[rr][ta * 4]);
+      // lasso codes are mostly zeros: skip the row when the warp's two atom quads are empty
+      if (__all_sync(0xffffffffu, a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f)) continue;
       const float4 b = *reinterpret_cast<const float4*>(&Bs[rr][tb * 4]);
       const float av[4] = {a.x, a.y, a.z, a.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
@@ -230,8 +237,12 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ z,
     for (int j = 0; j < 4; ++j) {
       const int a = a0 + ta * 4 + i, c = c0 + tb * 4 + j;
       if (a >= k || acc[i][j] == 0.f) continue;
-      if (c < k) atomicAdd(&gzz[(int64_t)a * k + c], (double)acc[i][j]);
-      else if (c < k + d) atomicAdd(&gzx[(int64_t)a * d + (c - k)], (double)acc[i][j]);
+      if (c < k) {
+        atomicAdd(&gzz[(int64_t)a * k + c], (double)acc[i][j]);
+        if (mirror) atomicAdd(&gzz[(int64_t)c * k + a], (double)acc[i][j]);
+      } else if (c < k + d) {
+        atomicAdd(&gzx[(int64_t)a * d + (c - k)], (double)acc[i][j]);
+      }
     }
 }
 
