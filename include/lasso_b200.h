@@ -43,7 +43,7 @@ typedef enum lasso_b200_path {
   LASSO_B200_PATH_AUTO = 0,    /* resident tcgen05 kernel when the shape fits, else FFMA     */
   LASSO_B200_PATH_FFMA = 1,    /* CUDA-core fp32 FFMA kernel: any n, d, k                    */
   LASSO_B200_PATH_TCGEN05 = 2, /* streaming tcgen05 kernel, one launch per iteration (bf16x3) */
-  LASSO_B200_PATH_RESIDENT = 3 /* resident tcgen05 kernel: all iterations of a 128-row tile on
+  LASSO_B200_PATH_RESIDENT = 3 /* resident tcgen05 kernel (any d <= 64, k <= 256): all iterations of a 128-row tile on
                                   chip in ONE launch (fp16x2 operand split of the rescaled
                                   problem).  Synchronises the stream once per solve; falls
                                   back to LASSO_B200_PATH_TCGEN05 by itself if an iterate

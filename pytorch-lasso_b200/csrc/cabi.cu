@@ -240,7 +240,7 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
     }
     g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
     z0 = z_start;
-    path = LASSO_B200_PATH_TCGEN05;
+    path = fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
   }
 
   // z_i lives in (i even ? z_a : z_b); put z_maxiter into z_out without a copy
@@ -406,7 +406,7 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
       finished = true;
     } else if (fell_back) {
       g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
-      path = LASSO_B200_PATH_TCGEN05;
+      path = fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
     }
   }
   if (!finished) {

@@ -80,6 +80,7 @@ struct ResParams {
   volatile int* dbg;        // host-mapped debug record or nullptr
   unsigned long long* trace;   // LASSO_B200_TRACE: per-warp (clock << 8 | event) log of block 0
   float limit;              // |operand| at which the solve is handed to the streaming kernel
+  bool vec_x, vec_z0, vec_z; // rows of x / z0 / z_out are 16-byte aligned (float4 access)
 };
 
 __device__ __noinline__ void res_wait_slow_path(uint64_t& t0, volatile int* dbg, int line, uint32_t parity) {
@@ -154,6 +155,27 @@ __device__ __forceinline__ uint32_t x_off(uint32_t row, uint32_t chunk) {
   return row * 256u + ((chunk ^ (row & 7u)) << 4);
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// 4 consecutive floats of a row of `cols` entries starting at column c (zero beyond the row);
+// vec = rows are 16-byte aligned (cols % 4 == 0 and an aligned base), else element by element
+__device__ __forceinline__ float4 load4(const float* __restrict__ rowp, int c, int cols, bool vec) {
+  if (vec) return __ldg(reinterpret_cast<const float4*>(rowp + c));
+  float4 v;
+  v.x = c + 0 < cols ? __ldg(rowp + c + 0) : 0.f;
+  v.y = c + 1 < cols ? __ldg(rowp + c + 1) : 0.f;
+  v.z = c + 2 < cols ? __ldg(rowp + c + 2) : 0.f;
+  v.w = c + 3 < cols ? __ldg(rowp + c + 3) : 0.f;
+  return v;
+}
+__device__ __forceinline__ void store4(float* __restrict__ rowp, int c, int cols, bool vec, float4 v) {
+  if (vec) {
+    *reinterpret_cast<float4*>(rowp + c) = v;
+    return;
+  }
+  if (c + 0 < cols) rowp[c + 0] = v.x;
+  if (c + 1 < cols) rowp[c + 1] = v.y;
+  if (c + 2 < cols) rowp[c + 2] = v.z;
+  if (c + 3 < cols) rowp[c + 3] = v.w;
+}
 
 // Schedule of one iteration (NQ = 4 chunks of 64 atoms; all 16 compute warps work on the same
 // chunk, each thread on 16 atoms of one row):
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       for (int i = 0; i < 4; ++i) {
         const int idx = ct + i * 512, r = idx >> 4, c4 = idx & 15;   // 16 consecutive lanes share a row
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < valid && c4 * 4 < p.d) v = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.d + c4 * 4));
+        if (r < valid && c4 * 4 < p.d) v = load4(p.x + (row0 + r) * p.d, c4 * 4, p.d, p.vec_x);
         float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -371,7 +393,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.z0 != nullptr && r < valid && c4 * 4 < p.k) {
-          v = __ldg(reinterpret_cast<const float4*>(p.z0 + (row0 + r) * p.k + c4 * 4));
+          v = load4(p.z0 + (row0 + r) * p.k, c4 * 4, p.k, p.vec_z0);
           const float szr = row_sx[r] * sc.isw;
           v.x *= szr; v.y *= szr; v.z *= szr; v.w *= szr;
         }
@@ -509,7 +531,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           bad |= !(fabsf(v.x) < p.limit) || !(fabsf(v.y) < p.limit) || !(fabsf(v.z) < p.limit) || !(fabsf(v.w) < p.limit);
           const float uzr = sc.sw / row_sx[r];
           v.x *= uzr; v.y *= uzr; v.z *= uzr; v.w *= uzr;
-          *reinterpret_cast<float4*>(p.z_out + (row0 + r) * p.k + c4 * 4) = v;
+          store4(p.z_out + (row0 + r) * p.k, c4 * 4, p.k, p.vec_z, v);
         }
       }
       compute_sync();
@@ -588,8 +610,9 @@ ResState g_res[64];
 }  // namespace
 
 bool fista_res_supported(int64_t n, int d, int k) {
-  return n >= 1 && d >= 4 && d <= kDP && k >= 4 && k <= kKP && (d % 4) == 0 && (k % 4) == 0 &&
-         n < (int64_t)1 << 31;
+  // any d <= 64, k <= 256: the dictionary image is zero padded and unaligned rows of x / z are
+  // read and written element by element (only at tile load / store, once per solve)
+  return n >= 1 && d >= 1 && d <= kDP && k >= 1 && k <= kKP && n < (int64_t)1 << 31;
 }
 
 // ---- host side: prepare (dictionary image, scalars, momentum table) / launch (a row range) /
@@ -691,6 +714,9 @@ int fista_res_launch(const float* x, const float* z0, float* z_out, int64_t n, i
   p.flag = S.flag;
   p.dbg = S.dbg_dev;
   p.trace = trace_path ? S.trace : nullptr;
+  p.vec_x = (d % 4) == 0 && ((uintptr_t)x % 16) == 0;
+  p.vec_z0 = (k % 4) == 0 && ((uintptr_t)z0 % 16) == 0;
+  p.vec_z = (k % 4) == 0 && ((uintptr_t)z_out % 16) == 0;
   p.limit = kPieceLimit;
   if (const char* lim = getenv("LASSO_B200_RES_LIMIT")) p.limit = (float)atof(lim);   // tests: force the fallback
 #define LASSO_RES_LAUNCH(NQ_)                                                               \

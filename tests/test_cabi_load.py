@@ -41,7 +41,8 @@ def test_no_torch_types_in_the_abi():
 def test_select_path_is_callable_without_gpu(build_extension):
     cabi = build_extension._cabi
     assert cabi.select_path(65536, 64, 256) == cabi.PATH_RESIDENT
-    assert cabi.select_path(128, 10, 50) == cabi.PATH_FFMA
+    assert cabi.select_path(128, 10, 50) == cabi.PATH_RESIDENT
+    assert cabi.select_path(128, 150, 90) == cabi.PATH_FFMA
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without GPU")

@@ -24,8 +24,12 @@ def _tc_shape(d, k):
 
 
 def _skip_unless_supported(path, d, k):
-    if path in ("tcgen05", "resident") and not _tc_shape(d, k):
-        pytest.skip("the tcgen05 kernels do not take d={} k={} (auto routes it to FFMA)".format(d, k))
+    # the streaming tcgen05 kernel moves rows by TMA (16-byte aligned rows: d, k multiples of 4);
+    # the resident kernel takes any d <= 64, k <= 256, larger shapes go to FFMA
+    if path == "tcgen05" and not _tc_shape(d, k):
+        pytest.skip("the streaming tcgen05 kernel does not take d={} k={}".format(d, k))
+    if path == "resident" and not (d <= 64 and k <= 256):
+        pytest.skip("the resident kernel does not take d={} k={}".format(d, k))
 
 
 @pytest.fixture(scope="module")
@@ -79,7 +83,7 @@ def test_early_stop_count_and_history(dev, path):
 
 @pytest.mark.parametrize("path", PATHS)
 def test_host_entry_point_equals_device_entry_point(dev, path):
-    g = load_golden("ista_ragged" if path == "ffma" else "ista_warmstart")
+    g = load_golden("ista_warmstart" if path == "tcgen05" else "ista_ragged")
     zd = run_case(g, dev, path)
     zh = ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=True, lr=g["lr"],
               maxiter=int(g["maxiter"]), tol=g["tol"], path=path)
@@ -94,7 +98,7 @@ def test_host_entry_point_equals_device_entry_point(dev, path):
 @pytest.mark.parametrize("path", PATHS)
 def test_edge_cases(dev, path):
     # ragged shape for the FFMA kernel, the nearest shape the tcgen05 kernels take otherwise
-    d, k = (7, 19) if path == "ffma" else (8, 20)
+    d, k = (8, 20) if path == "tcgen05" else (7, 19)
     x, w = make_problem(33, d, k, seed=2)
     xd, wd = x.to(dev), w.to(dev)
     lr = 1.0 / oracle.lipschitz_constant(w)
@@ -145,7 +149,8 @@ def test_deterministic_and_shard_invariant(dev, path):
 
 def test_auto_takes_the_resident_kernel(dev):
     assert _cabi.select_path(65536, 64, 256) == _cabi.PATH_RESIDENT
-    assert _cabi.select_path(128, 10, 50) == _cabi.PATH_FFMA        # d % 4 != 0
+    assert _cabi.select_path(128, 10, 50) == _cabi.PATH_RESIDENT    # unaligned rows are fine
+    assert _cabi.select_path(128, 65, 50) == _cabi.PATH_FFMA        # d > 64
     assert _cabi.select_path(1000, 128, 1024) == _cabi.PATH_FFMA    # C3: dictionary exceeds one SM
 
 
