@@ -293,6 +293,95 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   return LASSO_B200_OK;
 }
 
+}  // extern "C" (reopened below)
+
+namespace lasso {
+namespace {
+
+// Resident solve of a host-resident batch: the batch is cut into waves (one tile per SM) that
+// flow through a three-stage pipeline -- H2D of x (and z0) on one copy stream, the solve on the
+// compute stream, D2H of the codes on a second copy stream -- through a ring of kPipeSlots wave
+// buffers.  All but the first upload and the last download hide behind the kernels, and the
+// device footprint is kPipeSlots waves whatever n is (host batches larger than HBM stream through).
+// hist (device, [iters]) accumulates the stop-test record of all waves.  *fell_back = 1: an iterate
+// left the fp16 range somewhere; the caller must redo the batch on another path.
+constexpr int kPipeSlots = 3;
+int host_pipeline(const float* x, const float* z0, float* z_out, const float* dw, int64_t n, int d, int k,
+                  float lr_f, float lam_f, int iters, int fast, double* hist, int hist_mode, int* fell_back) {
+  int dev = 0, rc;
+  LASSO_CUDA_TRY(cudaGetDevice(&dev));
+  HostPipe& hp = g_pipe[dev];
+  cudaStream_t st = nullptr;
+  if (!hp.s_in) {
+    LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+  }
+  const int64_t wave = fista_res_wave_rows(n), trows = fista_res_tile_rows(n);
+  const int64_t nchunks = (n + wave - 1) / wave;
+  const int slots = (int)std::min<int64_t>(kPipeSlots, nchunks);
+  float *dx, *dz;
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace* ws = nullptr;
+    if ((rc = current_workspace(&ws))) return rc;
+    if ((rc = ensure(ws->hx, sizeof(float) * (size_t)slots * wave * d))) return rc;
+    if ((rc = ensure(ws->hz, sizeof(float) * (size_t)slots * wave * k))) return rc;
+    dx = (float*)ws->hx.ptr;
+    dz = (float*)ws->hz.ptr;
+  }
+  while ((int)hp.events.size() < 3 * kPipeSlots + 1) {
+    cudaEvent_t ev;
+    LASSO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    hp.events.push_back(ev);
+  }
+  // events: [3 s] chunk in slot s uploaded, [3 s + 1] solved, [3 s + 2] downloaded; [last] start
+  cudaEvent_t ev_start = hp.events[3 * kPipeSlots];
+  if ((rc = fista_res_prepare(dw, d, k, lr_f, lam_f, iters, fast, st))) return rc;
+  if (hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)iters, st));
+  // the copy streams must not run ahead of work of an earlier call still queued on `st`
+  LASSO_CUDA_TRY(cudaEventRecord(ev_start, st));
+  LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, ev_start, 0));
+  LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, ev_start, 0));
+  auto upload = [&](int64_t c) -> int {
+    const int s = (int)(c % slots);
+    const int64_t r0 = c * wave, rows = std::min<int64_t>(wave, n - r0);
+    // the slot's previous tenant (chunk c - slots) must have been downloaded
+    if (c >= slots) LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.events[3 * s + 2], 0));
+    LASSO_CUDA_TRY(cudaMemcpyAsync(dx + (int64_t)s * wave * d, x + r0 * d, sizeof(float) * (size_t)rows * d,
+                                   cudaMemcpyHostToDevice, hp.s_in));
+    if (z0)
+      LASSO_CUDA_TRY(cudaMemcpyAsync(dz + (int64_t)s * wave * k, z0 + r0 * k, sizeof(float) * (size_t)rows * k,
+                                     cudaMemcpyHostToDevice, hp.s_in));
+    LASSO_CUDA_TRY(cudaEventRecord(hp.events[3 * s], hp.s_in));
+    return LASSO_B200_OK;
+  };
+  for (int64_t c = 0; c < slots; ++c)
+    if ((rc = upload(c))) return rc;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int s = (int)(c % slots);
+    const int64_t r0 = c * wave, rows = std::min<int64_t>(wave, n - r0);
+    float* zc = dz + (int64_t)s * wave * k;
+    LASSO_CUDA_TRY(cudaStreamWaitEvent(st, hp.events[3 * s], 0));
+    if ((rc = fista_res_launch(dx + (int64_t)s * wave * d, z0 ? zc : nullptr, zc, rows, d, k, iters, hist,
+                               hist_mode, trows, st)))
+      return rc;
+    LASSO_CUDA_TRY(cudaEventRecord(hp.events[3 * s + 1], st));
+    LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.events[3 * s + 1], 0));
+    LASSO_CUDA_TRY(cudaMemcpyAsync(z_out + r0 * k, zc, sizeof(float) * (size_t)rows * k,
+                                   cudaMemcpyDeviceToHost, hp.s_out));
+    LASSO_CUDA_TRY(cudaEventRecord(hp.events[3 * s + 2], hp.s_out));
+    if (c + slots < nchunks && (rc = upload(c + slots))) return rc;
+  }
+  if ((rc = fista_res_finish(fell_back, st))) return rc;
+  LASSO_CUDA_TRY(cudaStreamSynchronize(hp.s_out));
+  return LASSO_B200_OK;
+}
+
+}  // namespace
+}  // namespace lasso
+
+extern "C" {
+
 int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const float* z0,
                                   float* z_out, int64_t n, int32_t d, int32_t k, double alpha,
                                   double lr, int32_t maxiter, int32_t fast, double tol_abs,
@@ -310,122 +399,84 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
   }
   const size_t xb = sizeof(float) * (size_t)n * d, wb = sizeof(float) * (size_t)d * k;
   const size_t zb = sizeof(float) * (size_t)n * k;
-  float *dx, *dw, *dz;
+  cudaStream_t st = nullptr;  // legacy default stream: ordered with the copies below
+  int done = maxiter;
+  float* dw;
+  double* hist;
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace* ws = nullptr;
+    if ((rc = current_workspace(&ws))) return rc;
+    if ((rc = ensure(ws->hw, wb))) return rc;
+    if ((rc = ensure(ws->hist, sizeof(double) * (size_t)(maxiter + 1)))) return rc;
+    dw = (float*)ws->hw.ptr;
+    hist = (double*)ws->hist.ptr;
+  }
+
+  const int resolved = path == LASSO_B200_PATH_AUTO ? lasso_b200_select_path(n, d, k) : path;
+  if (resolved == LASSO_B200_PATH_RESIDENT && fista_res_supported(n, d, k) && maxiter > 0 &&
+      std::isfinite(lr) && lr > 0.0 && std::isfinite(alpha)) {
+    const bool need_hist = tol_abs >= 0.0 || delta_hist != nullptr;
+    // a threshold of exactly 0 only asks whether anything moved; the sums are not needed then
+    const int hist_mode = !need_hist ? 0 : ((delta_hist == nullptr && tol_abs == 0.0) ? 2 : 1);
+    const float lr_f = (float)lr, lam_f = (float)(alpha * lr);
+    LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
+    int fell_back = 0, run_iters = maxiter;
+    for (int pass = 0; pass < 2; ++pass) {
+      if ((rc = host_pipeline(x, z0, z_out, dw, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
+                              need_hist ? hist : nullptr, hist_mode, &fell_back)))
+        return rc;
+      if (fell_back || pass == 1 || tol_abs < 0.0 || run_iters <= 1) break;
+      // the stop test is batch-global (ista.py:93): take it from the recorded sums and, if it fired
+      // before maxiter, stream the batch through once more with exactly that many iterations
+      std::vector<double> h((size_t)run_iters);
+      LASSO_CUDA_TRY(cudaMemcpy(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+      int stop = run_iters;
+      for (int i = 0; i + 1 < run_iters; ++i)
+        if (h[(size_t)i] <= tol_abs) {
+          stop = i + 1;
+          break;
+        }
+      if (stop == run_iters) break;
+      run_iters = stop;
+    }
+    if (!fell_back) {
+      if (delta_hist) {
+        std::vector<double> h((size_t)maxiter, 0.0);
+        LASSO_CUDA_TRY(cudaMemcpy(h.data(), hist, sizeof(double) * (size_t)run_iters, cudaMemcpyDeviceToHost));
+        memcpy(delta_hist, h.data(), sizeof(double) * (size_t)maxiter);
+      }
+      if (iters_done) *iters_done = run_iters;
+      return LASSO_B200_OK;
+    }
+    g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
+    path = fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
+  }
+
+  // plain copy - solve - copy (streaming kernels; whole batch on the device)
+  float *dx, *dz;
   double* dh = nullptr;
   {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     Workspace* ws = nullptr;
     if ((rc = current_workspace(&ws))) return rc;
     if ((rc = ensure(ws->hx, xb))) return rc;
-    if ((rc = ensure(ws->hw, wb))) return rc;
     if ((rc = ensure(ws->hz, zb + sizeof(double) * (size_t)(maxiter + 1)))) return rc;
     dx = (float*)ws->hx.ptr;
-    dw = (float*)ws->hw.ptr;
     dz = (float*)ws->hz.ptr;
     if (delta_hist) dh = (double*)((char*)ws->hz.ptr + ((zb + 7) & ~(size_t)7));
   }
-  cudaStream_t st = nullptr;  // legacy default stream: ordered with the copies below
-  int done = maxiter;
-
-  // Resident kernel: the batch is cut into waves (one tile per SM) that flow through a
-  // three-stage pipeline -- H2D of x on one copy stream, the solve on the compute stream, D2H of
-  // the codes on a second copy stream -- so that all but the first upload and the last download
-  // hide behind the kernels.  A stop test that fired early, or a hand-over to the streaming
-  // kernel, falls through to the plain copy-solve-copy sequence below (z0 is re-read from the host).
-  const int resolved = path == LASSO_B200_PATH_AUTO ? lasso_b200_select_path(n, d, k) : path;
-  bool finished = false, replay = false;
-  if (resolved == LASSO_B200_PATH_RESIDENT && fista_res_supported(n, d, k) && maxiter > 0 &&
-      std::isfinite(lr) && lr > 0.0 && std::isfinite(alpha)) {
-    int dev = 0;
-    LASSO_CUDA_TRY(cudaGetDevice(&dev));
-    HostPipe& hp = g_pipe[dev];
-    if (!hp.s_in) {
-      LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
-      LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
-    }
-    double* hist = nullptr;
-    {
-      std::lock_guard<std::mutex> lock(g_ws_mutex);
-      Workspace* ws = nullptr;
-      if ((rc = current_workspace(&ws))) return rc;
-      if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
-      hist = (double*)ws->hist.ptr;
-    }
-    const bool need_hist = tol_abs >= 0.0 || delta_hist != nullptr;
-    const int hist_mode = !need_hist ? 0 : ((delta_hist == nullptr && tol_abs == 0.0) ? 2 : 1);
-    const int64_t wave = fista_res_wave_rows(n);
-    const int64_t nchunks = (n + wave - 1) / wave;
-    while ((int64_t)hp.events.size() < 2 * nchunks) {
-      cudaEvent_t ev;
-      LASSO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      hp.events.push_back(ev);
-    }
-    LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
-    if ((rc = fista_res_prepare(dw, d, k, (float)lr, (float)(alpha * lr), maxiter, fast ? 1 : 0, st))) return rc;
-    if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
-    // the copy streams must not run ahead of work of an earlier call still queued on `st`
-    LASSO_CUDA_TRY(cudaEventRecord(hp.events[0], st));
-    LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.events[0], 0));
-    LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.events[0], 0));
-    for (int64_t c = 0; c < nchunks; ++c) {
-      const int64_t r0 = c * wave, rows = std::min<int64_t>(wave, n - r0);
-      LASSO_CUDA_TRY(cudaMemcpyAsync(dx + r0 * d, x + r0 * d, sizeof(float) * (size_t)rows * d,
-                                     cudaMemcpyHostToDevice, hp.s_in));
-      if (z0)
-        LASSO_CUDA_TRY(cudaMemcpyAsync(dz + r0 * k, z0 + r0 * k, sizeof(float) * (size_t)rows * k,
-                                       cudaMemcpyHostToDevice, hp.s_in));
-      LASSO_CUDA_TRY(cudaEventRecord(hp.events[2 * c], hp.s_in));
-    }
-    for (int64_t c = 0; c < nchunks; ++c) {
-      const int64_t r0 = c * wave, rows = std::min<int64_t>(wave, n - r0);
-      LASSO_CUDA_TRY(cudaStreamWaitEvent(st, hp.events[2 * c], 0));
-      if ((rc = fista_res_launch(dx + r0 * d, z0 ? dz + r0 * k : nullptr, dz + r0 * k, rows, d, k, maxiter,
-                                 need_hist ? hist : nullptr, hist_mode, fista_res_tile_rows(n), st)))
-        return rc;
-      LASSO_CUDA_TRY(cudaEventRecord(hp.events[2 * c + 1], st));
-      LASSO_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.events[2 * c + 1], 0));
-      LASSO_CUDA_TRY(cudaMemcpyAsync(z_out + r0 * k, dz + r0 * k, sizeof(float) * (size_t)rows * k,
-                                     cudaMemcpyDeviceToHost, hp.s_out));
-    }
-    int fell_back = 0;
-    if ((rc = fista_res_finish(&fell_back, st))) return rc;
-    if (!fell_back && tol_abs >= 0.0 && maxiter > 1) {
-      std::vector<double> h((size_t)maxiter);
-      LASSO_CUDA_TRY(cudaMemcpy(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
-      for (int i = 0; i + 1 < maxiter; ++i)
-        if (h[(size_t)i] <= tol_abs) {
-          done = i + 1;
-          replay = true;
-          break;
-        }
-    }
-    LASSO_CUDA_TRY(cudaStreamSynchronize(hp.s_out));
-    if (!fell_back && !replay) {
-      if (delta_hist)
-        LASSO_CUDA_TRY(cudaMemcpy(delta_hist, hist, sizeof(double) * (size_t)maxiter, cudaMemcpyDeviceToHost));
-      finished = true;
-    } else if (fell_back) {
-      g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
-      path = fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
-    }
-  }
-  if (!finished) {
-    LASSO_CUDA_TRY(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, st));
-    LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
-    if (z0) LASSO_CUDA_TRY(cudaMemcpyAsync(dz, z0, zb, cudaMemcpyHostToDevice, st));
-    if (dh && maxiter > 0) LASSO_CUDA_TRY(cudaMemsetAsync(dh, 0, sizeof(double) * (size_t)maxiter, st));
-    // replay of a run whose stop test fired at iteration `done`: exactly that many iterations
-    int inner_done = maxiter;
-    rc = lasso_b200_fista_f32(dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, replay ? done : maxiter,
-                              fast, replay ? -1.0 : tol_abs, &inner_done, dh, path, st);
-    if (rc) return rc;
-    if (!replay) done = inner_done;
-    LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, dz, zb, cudaMemcpyDeviceToHost, st));
-    if (delta_hist && maxiter > 0)
-      LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, dh, sizeof(double) * (size_t)maxiter,
-                                     cudaMemcpyDeviceToHost, st));
-    LASSO_CUDA_TRY(cudaStreamSynchronize(st));
-  }
+  LASSO_CUDA_TRY(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, st));
+  LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
+  if (z0) LASSO_CUDA_TRY(cudaMemcpyAsync(dz, z0, zb, cudaMemcpyHostToDevice, st));
+  rc = lasso_b200_fista_f32(dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, maxiter, fast, tol_abs,
+                            &done, dh, path, st);
+  if (rc) return rc;
+  LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, dz, zb, cudaMemcpyDeviceToHost, st));
+  if (delta_hist && maxiter > 0)
+    LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, dh, sizeof(double) * (size_t)maxiter,
+                                   cudaMemcpyDeviceToHost, st));
+  LASSO_CUDA_TRY(cudaStreamSynchronize(st));
   if (iters_done) *iters_done = done;
   return LASSO_B200_OK;
 }

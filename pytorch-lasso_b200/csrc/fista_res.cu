@@ -177,6 +177,66 @@ __device__ __forceinline__ void store4(float* __restrict__ rowp, int c, int cols
   if (c + 3 < cols) rowp[c + 3] = v.w;
 }
 
+// Tile load / store live in their own (non-inlined) functions: they run once per tile and solve,
+// and kept inline they cost the iteration loop registers (6 % at C2).
+//
+// Row r is scaled by sx_r = 2^(6 - exponent(max |x_r|)) (max |x'_r| in [64, 128)); its codes then
+// live in units of sx_r / sw.  A row's result depends on that row alone, so any row split of a
+// batch gives the same bits.
+__device__ __noinline__ void res_load_tile(const ResParams& p, uint8_t* xs, uint8_t* zs, float* row_sx,
+                                           int64_t row0, int valid, float isw, int ct) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = ct + i * 512, r = idx >> 4, c4 = idx & 15;   // 16 consecutive lanes share a row
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < valid && c4 * 4 < p.d) v = load4(p.x + (row0 + r) * p.d, c4 * 4, p.d, p.vec_x);
+    float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // a non-finite row keeps scale 1, turns into inf / NaN codes and is caught at the store
+    float sxr = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+      // 2^(6 - e), e = unbiased exponent of m: biased exponent 127 + 6 - (E - 127)
+      const int be = 260 - (int)((__float_as_uint(m) >> 23) & 0xFFu);
+      sxr = __uint_as_float((uint32_t)min(max(be, 1), 254) << 23);
+    }
+    v.x *= sxr; v.y *= sxr; v.z *= sxr; v.w *= sxr;
+    *reinterpret_cast<float4*>(xs + x_off(r, c4)) = v;
+    if (c4 == 0) row_sx[r] = sxr;
+  }
+  compute_sync();
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.z0 != nullptr && r < valid && c4 * 4 < p.k) {
+      v = load4(p.z0 + (row0 + r) * p.k, c4 * 4, p.k, p.vec_z0);
+      const float szr = row_sx[r] * isw;
+      v.x *= szr; v.y *= szr; v.z *= szr; v.w *= szr;
+    }
+    *reinterpret_cast<float4*>(zs + z_off(r, c4)) = v;
+  }
+  compute_sync();
+}
+
+// returns true when a code is inf / NaN / beyond the limit: an operand left the fp16 range
+__device__ __noinline__ bool res_store_tile(const ResParams& p, const uint8_t* zs, const float* row_sx,
+                                            int64_t row0, int valid, float sw, int ct) {
+  bool bad = false;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
+    if (r < valid && c4 * 4 < p.k) {
+      float4 v = *reinterpret_cast<const float4*>(zs + z_off(r, c4));
+      bad |= !(fabsf(v.x) < p.limit) || !(fabsf(v.y) < p.limit) || !(fabsf(v.z) < p.limit) || !(fabsf(v.w) < p.limit);
+      const float uzr = sw / row_sx[r];
+      v.x *= uzr; v.y *= uzr; v.z *= uzr; v.w *= uzr;
+      store4(p.z_out + (row0 + r) * p.k, c4 * 4, p.k, p.vec_z, v);
+    }
+  }
+  return bad;
+}
+
 // Schedule of one iteration (NQ = 4 chunks of 64 atoms; all 16 compute warps work on the same
 // chunk, each thread on 16 atoms of one row):
 //
@@ -365,41 +425,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       int valid = p.trows;
       if (row0 + valid > p.n) valid = (int)(p.n - row0);
       // ---------------- load the tile: x and z0, rescaled per row ----------------
-      // Row r is scaled by sx_r = 2^(6 - exponent(max |x_r|)) (max |x'_r| in [64, 128)); its codes
-      // then live in units of sx_r / sw.  A row's result depends on that row alone, so any row
-      // split of a batch gives the same bits.
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = ct + i * 512, r = idx >> 4, c4 = idx & 15;   // 16 consecutive lanes share a row
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < valid && c4 * 4 < p.d) v = load4(p.x + (row0 + r) * p.d, c4 * 4, p.d, p.vec_x);
-        float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        // a non-finite row keeps scale 1, turns into inf / NaN codes and is caught at the store
-        float sxr = 1.f;
-        if (m > 0.f && m < 3.0e38f) {
-          // 2^(6 - e), e = unbiased exponent of m: biased exponent 127 + 6 - (E - 127)
-          const int be = 260 - (int)((__float_as_uint(m) >> 23) & 0xFFu);
-          sxr = __uint_as_float((uint32_t)min(max(be, 1), 254) << 23);
-        }
-        v.x *= sxr; v.y *= sxr; v.z *= sxr; v.w *= sxr;
-        *reinterpret_cast<float4*>(xs + x_off(r, c4)) = v;
-        if (c4 == 0) row_sx[r] = sxr;
-      }
-      compute_sync();
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.z0 != nullptr && r < valid && c4 * 4 < p.k) {
-          v = load4(p.z0 + (row0 + r) * p.k, c4 * 4, p.k, p.vec_z0);
-          const float szr = row_sx[r] * sc.isw;
-          v.x *= szr; v.y *= szr; v.z *= szr; v.w *= szr;
-        }
-        *reinterpret_cast<float4*>(zs + z_off(r, c4)) = v;
-      }
-      compute_sync();
+      res_load_tile(p, xs, zs, row_sx, row0, valid, sc.isw, ct);
       const float lam = sc.lam * row_sx[row];           // lam sx_r / sw
       const float uz_row = sc.sw / row_sx[row];         // code units -> caller units (exact)
       // ---------------- y_0 = z_0 (ista.py:76) and its pieces ----------------
@@ -522,18 +548,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       }
       // ---------------- store the codes ----------------
       compute_sync();
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int idx = ct + i * 512, r = idx >> 6, c4 = idx & 63;
-        if (r < valid && c4 * 4 < p.k) {
-          float4 v = *reinterpret_cast<const float4*>(zs + z_off(r, c4));
-          // an operand beyond the fp16 range turned into inf / NaN and stays that way
-          bad |= !(fabsf(v.x) < p.limit) || !(fabsf(v.y) < p.limit) || !(fabsf(v.z) < p.limit) || !(fabsf(v.w) < p.limit);
-          const float uzr = sc.sw / row_sx[r];
-          v.x *= uzr; v.y *= uzr; v.z *= uzr; v.w *= uzr;
-          store4(p.z_out + (row0 + r) * p.k, c4 * 4, p.k, p.vec_z, v);
-        }
-      }
+      bad |= res_store_tile(p, zs, row_sx, row0, valid, sc.sw, ct);
       compute_sync();
     }
     if (bad) atomicExch(p.flag, 1);

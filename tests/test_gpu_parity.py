@@ -210,6 +210,27 @@ def test_resident_falls_back_to_the_streaming_kernel(dev, monkeypatch):
     assert bool(torch.isfinite(got[:3]).all()) and bool(torch.isfinite(got[4:]).all())
 
 
+def test_host_pipeline_streams_waves_through_a_ring(dev):
+    # more waves than ring slots: chunk buffers are reused while earlier downloads are in flight;
+    # the result must equal the device entry point bit for bit, with a warm start and with a stop
+    # test that fires early (second pipelined pass with exactly that many iterations)
+    n, d, k = 90000, 16, 32
+    x, w = make_problem(n, d, k, seed=9)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    g = torch.Generator().manual_seed(3)
+    z0 = 0.05 * torch.randn(n, k, generator=g)
+    xd, wd = x.to(dev), w.to(dev)
+    want, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 12, True, -1.0, path="resident")
+    got, _ = _cabi.fista_host(x.pin_memory(), w, z0.pin_memory(), 0.1, lr, 12, True, -1.0, path="resident")
+    assert torch.equal(got, want.cpu())
+    tol_abs = float(np.float32(n * k * 1e-3))
+    want, done_d, _ = _cabi.fista_device(xd, wd, None, 0.1, lr, 300, True, tol_abs, path="resident",
+                                         want_iters=True)
+    got, done_h = _cabi.fista_host(x, w, None, 0.1, lr, 300, True, tol_abs, path="resident", want_iters=True)
+    assert 1 < done_d < 300 and done_h == done_d
+    assert torch.equal(got, want.cpu())
+
+
 def test_resident_zero_threshold_stop_test(dev):
     # tol = 0 keeps the reference's stop test armed: it fires when an iteration changes nothing
     # (ista.py:93 with a threshold of 0).  The resident kernel records only "moved / did not move".
