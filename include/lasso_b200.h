@@ -40,14 +40,19 @@ typedef enum lasso_b200_status {
 
 /* which inner-loop kernel lasso_b200_fista_f32 uses */
 typedef enum lasso_b200_path {
-  LASSO_B200_PATH_AUTO = 0,    /* resident tcgen05 kernel when the shape fits, else FFMA     */
+  LASSO_B200_PATH_AUTO = 0,    /* resident, else k-blocked tcgen05 kernel when the shape fits, else FFMA */
   LASSO_B200_PATH_FFMA = 1,    /* CUDA-core fp32 FFMA kernel: any n, d, k                    */
   LASSO_B200_PATH_TCGEN05 = 2, /* streaming tcgen05 kernel, one launch per iteration (bf16x3) */
-  LASSO_B200_PATH_RESIDENT = 3 /* resident tcgen05 kernel (any d <= 64, k <= 256): all iterations of a 128-row tile on
-                                  chip in ONE launch (fp16x2 operand split of the rescaled
+  LASSO_B200_PATH_RESIDENT = 3, /* resident tcgen05 kernel (any d <= 64, k <= 256): all iterations
+                                  of a 128-row tile on chip in ONE launch (fp16x2 operand split of the rescaled
                                   problem).  Synchronises the stream once per solve; falls
                                   back to LASSO_B200_PATH_TCGEN05 by itself if an iterate
                                   leaves the fp16 operand range.                               */
+  LASSO_B200_PATH_BLOCKED = 4  /* k-blocked streaming tcgen05 kernel for dictionaries that do not
+                                  fit one SM (d <= 128, k <= 1024, multiples of 4): one launch per
+                                  iteration, codes and dictionary slices stream through a TMA
+                                  ring.  Synchronises the stream once per solve; falls back to
+                                  LASSO_B200_PATH_FFMA by itself like the resident path.        */
 } lasso_b200_path;
 
 /* ABI version: major*1000 + minor */

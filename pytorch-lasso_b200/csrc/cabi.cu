@@ -146,7 +146,8 @@ int64_t lasso_b200_resident_fallbacks(void) { return (int64_t)g_res_fallbacks.lo
 
 int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k) {
   if (fista_res_supported(n, d, k)) return LASSO_B200_PATH_RESIDENT;
-  return fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
+  if (fista_tc_supported(n, d, k)) return LASSO_B200_PATH_TCGEN05;
+  return fista_blk_supported(n, d, k) ? LASSO_B200_PATH_BLOCKED : LASSO_B200_PATH_FFMA;
 }
 
 int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z0, float* z_out,
@@ -166,12 +167,13 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   }
   if (path == LASSO_B200_PATH_AUTO) path = lasso_b200_select_path(n, d, k);
   if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05 &&
-      path != LASSO_B200_PATH_RESIDENT) {
+      path != LASSO_B200_PATH_RESIDENT && path != LASSO_B200_PATH_BLOCKED) {
     set_error("unknown path %d", path);
     return LASSO_B200_ERR_INVALID;
   }
   if ((path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) ||
-      (path == LASSO_B200_PATH_RESIDENT && !fista_res_supported(n, d, k))) {
+      (path == LASSO_B200_PATH_RESIDENT && !fista_res_supported(n, d, k)) ||
+      (path == LASSO_B200_PATH_BLOCKED && !fista_blk_supported(n, d, k))) {
     set_error("tcgen05 paths do not take n=%lld d=%d k=%d", (long long)n, d, k);
     return LASSO_B200_ERR_UNSUPPORTED;
   }
@@ -266,7 +268,28 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   a.fast = fast ? 1 : 0;
   a.tol_abs = tol_abs;
   a.hist = hist;
-  rc = (path == LASSO_B200_PATH_TCGEN05) ? fista_tc_run(a, z_out, st) : fista_ffma_run(a, z_out, st);
+  if (path == LASSO_B200_PATH_BLOCKED) {
+    // like the resident path: an iterate beyond the fp16 operand range hands the batch to the FFMA
+    // kernel, which needs the start codes again (they may alias z_out)
+    float* stash = nullptr;
+    if (z0 != nullptr && z0 == z_out) {
+      LASSO_CUDA_TRY(cudaMallocAsync((void**)&stash, code_bytes, st));
+      LASSO_CUDA_TRY(cudaMemcpyAsync(stash, z_a, code_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    int fell_back = 0;
+    rc = fista_blk_run(a, &fell_back, st);
+    if (!rc && fell_back) {
+      g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
+      const float* src = stash ? stash : z0;
+      if (src == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_a, 0, code_bytes, st));
+      else if (src != z_a) LASSO_CUDA_TRY(cudaMemcpyAsync(z_a, src, code_bytes, cudaMemcpyDeviceToDevice, st));
+      LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+      rc = fista_ffma_run(a, z_out, st);
+    }
+    if (stash) cudaFreeAsync(stash, st);
+  } else {
+    rc = (path == LASSO_B200_PATH_TCGEN05) ? fista_tc_run(a, z_out, st) : fista_ffma_run(a, z_out, st);
+  }
   if (rc) return rc;
 
   int* ctl = (int*)ws->ctl.ptr;
