@@ -19,7 +19,7 @@
 // iterate left the fp16 range.
 //
 // HBM traffic per iteration: n (d + 5 k) floats (both code buffers are read in both passes).
-// TMEM columns: R 128 | r pieces 128 | G 64 | 2 piece slots x 64 = 448 of 512.
+// TMEM columns: R_big 128 | R_small 128 | r pieces 128 | G 64 | piece slot 64 = 512.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -48,10 +48,13 @@ constexpr uint32_t kStageBytes = 2 * kZChunkBytes + kWSliceBytes;   // z_cur, z_
 constexpr int kStagesB = 2;
 constexpr uint32_t kSmemBytesB = kStagesB * kStageBytes;            // 192 KB
 
-constexpr uint32_t kColR = 0;       // R = Y W^T, 128 features
-constexpr uint32_t kColRp = 128;    // r pieces: h 64 cols | l 64 cols
-constexpr uint32_t kColG = 256;     // G chunk, 64 atoms
-constexpr uint32_t kColS = 320;     // piece slots: 2 x [h 32 cols | l 32 cols]
+constexpr uint32_t kColR = 0;       // R_big   = sum of the leading products h h' (128 features)
+constexpr uint32_t kColRs = 128;    // R_small = sum of the cross products h l' + l h'.  Two accumulators:
+                                    // the tensor core truncates on every accumulate and with k = 1024
+                                    // (192 accumulations) a single one costs a factor 2-3 in accuracy
+constexpr uint32_t kColRp = 256;    // r pieces: h 64 cols | l 64 cols
+constexpr uint32_t kColG = 384;     // G chunk, 64 atoms
+constexpr uint32_t kColS = 448;     // piece slot: [h 32 cols | l 32 cols]
 constexpr uint32_t kTmemColsB = 512;
 
 struct BlkScalars {
@@ -69,6 +72,7 @@ struct BlkParams {
   int d, k;
   float beta;
   int use_prev;
+  int trows;                // rows per tile: 128 (64 for experiments: half of the MMA rows idle)
   const BlkScalars* scal;
   StepCtl ctl;
   volatile int* dbg;
@@ -124,7 +128,7 @@ __device__ __forceinline__ void bsplit2(float2 v, uint32_t& wh, uint32_t& wl) {
 __global__ void __launch_bounds__(kThreadsB, 1)
 fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__ CUtensorMap tm_prev, BlkParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_full[kStagesB], bar_empty[kStagesB], bar_aready[2], bar_sfree[2];
+  __shared__ uint64_t bar_full[kStagesB], bar_empty[kStagesB], bar_aready, bar_sfree;
   __shared__ uint64_t bar_rfull, bar_rready, bar_gfull, bar_gfree;
   __shared__ uint32_t tmem_base_s;
 
@@ -134,7 +138,8 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nq = (p.k + kQ - 1) / kQ;
   const int dsteps = (p.d + 15) >> 4;
-  const int ntiles = (int)((p.n + kTileM - 1) / kTileM);
+  const int trows = p.trows;
+  const int ntiles = (int)((p.n + trows - 1) / trows);
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
@@ -142,10 +147,8 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 513);   // 512 compute threads (done reading z) + 1 MMA commit (done reading W)
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_aready[s], 512);
-      mbar_init(&bar_sfree[s], 1);
-    }
+    mbar_init(&bar_aready, 512);
+    mbar_init(&bar_sfree, 1);
     mbar_init(&bar_rfull, 1);
     mbar_init(&bar_rready, 512);
     mbar_init(&bar_gfull, 1);
@@ -170,14 +173,15 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
     __syncwarp();
     uint32_t cc = 0;   // chunk loads issued (2 nq per tile)
     for (int tile = 0; tile < my_tiles; ++tile) {
-      const int row0 = ((int)blockIdx.x + tile * (int)gridDim.x) * kTileM;
+      const int row0 = ((int)blockIdx.x + tile * (int)gridDim.x) * trows;
+      const uint32_t box_bytes = (uint32_t)trows * 128u;
       for (int pass = 0; pass < 2; ++pass) {
         for (int q = 0; q < nq; ++q, ++cc) {
           const uint32_t s = cc & 1u, ph = (cc >> 1) & 1u;
           BLK_WAIT(&bar_empty[s], ph ^ 1u);
           if (elect_one()) {
             uint8_t* st = smem + s * kStageBytes;
-            mbar_expect_tx(&bar_full[s], kStageBytes);
+            mbar_expect_tx(&bar_full[s], 4u * box_bytes + kWSliceBytes);
             tma_load_2d(st, &tm_cur, q * kQ, row0, &bar_full[s]);
             tma_load_2d(st + kBoxBytes, &tm_cur, q * kQ + 32, row0, &bar_full[s]);
             tma_load_2d(st + kZChunkBytes, &tm_prev, q * kQ, row0, &bar_full[s]);
@@ -198,24 +202,25 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
     for (int tile = 0; tile < my_tiles; ++tile, ++ti) {
       // ---- pass 1: GEMM1 slices ----
       for (int q = 0; q < nq; ++q, ++cc, ++pc) {
-        const uint32_t s = cc & 1u, slot = pc & 1u;
+        const uint32_t s = cc & 1u;
         BLK_WAIT(&bar_full[s], (cc >> 1) & 1u);       // dictionary slice landed
-        BLK_WAIT(&bar_aready[slot], (pc >> 1) & 1u);  // pieces of y_q staged
+        BLK_WAIT(&bar_aready, pc & 1u);               // pieces of y_q staged
         tc_fence_after();
         if (elect_one()) {
           const uint64_t desc = make_smem_desc_sw128(smem_u32(smem + s * kStageBytes + 2 * kZChunkBytes), 0, 1024);
           const uint32_t d_lo = (uint32_t)desc, d_hi = (uint32_t)(desc >> 32);
-          const uint32_t t_slot = tbase + kColS + slot * 64;
+          const uint32_t t_slot = tbase + kColS;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t qh = ((uint64_t)d_hi << 32) | (d_lo + ks * 2);
             const uint64_t ql = ((uint64_t)d_hi << 32) | (d_lo + ks * 2 + kPiece16);
             const uint32_t ah = t_slot + ks * 8, al = ah + 32;
-            mma_ts<false>(tbase + kColR, ah, ql, idesc1, (q > 0 || ks > 0) ? 1u : 0u);
-            mma_ts<false>(tbase + kColR, al, qh, idesc1, 1);
-            mma_ts<false>(tbase + kColR, ah, qh, idesc1, 1);
+            const uint32_t acc_on = (q > 0 || ks > 0) ? 1u : 0u;
+            mma_ts<false>(tbase + kColRs, ah, ql, idesc1, acc_on);
+            mma_ts<false>(tbase + kColRs, al, qh, idesc1, 1);
+            mma_ts<false>(tbase + kColR, ah, qh, idesc1, acc_on);
           }
-          mma_commit(&bar_sfree[slot]);
+          mma_commit(&bar_sfree);
           mma_commit(&bar_empty[s]);
           if (q == nq - 1) mma_commit(&bar_rfull);
         }
@@ -266,14 +271,14 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
     uint32_t cc = 0, pc = 0, gc = 0, ti = 0;
     double dsum = 0.0;
     for (int tile = 0; tile < my_tiles; ++tile, ++ti) {
-      const int64_t grow = (int64_t)((int)blockIdx.x + tile * (int)gridDim.x) * kTileM + row;
-      const bool row_ok = grow < p.n;
+      const int64_t grow = (int64_t)((int)blockIdx.x + tile * (int)gridDim.x) * trows + row;
+      const bool row_ok = row < trows && grow < p.n;
       const float sxr = row_ok ? __ldg(p.row_scale + grow) : 1.f;
       const float lam = sc.lam * sxr;
       const float uz_row = sc.sw / sxr;
       // ---------------- pass 1: y chunks -> pieces ----------------
       for (int q = 0; q < nq; ++q, ++cc, ++pc) {
-        const uint32_t s = cc & 1u, slot = pc & 1u;
+        const uint32_t s = cc & 1u;
         BLK_WAIT(&bar_full[s], (cc >> 1) & 1u);
         const uint8_t* zc_s = smem + s * kStageBytes + zbox;
         const uint8_t* zp_s = zc_s + kZChunkBytes;
@@ -292,16 +297,16 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
           bsplit2(yb, wh[2 * j + 1], wl[2 * j + 1]);
         }
         mbar_arrive(&bar_empty[s]);                       // done reading the stage
-        if (pc >= 2) BLK_WAIT(&bar_sfree[slot], ((pc >> 1) - 1u) & 1u);   // slot consumed by GEMM1 of chunk pc - 2
+        if (pc >= 1) BLK_WAIT(&bar_sfree, (pc - 1u) & 1u);   // slot consumed by the GEMM1 slice before
         tc_fence_after();
-        const uint32_t t_slot = tbase + lane_base + kColS + slot * 64 + wg * 8;
+        const uint32_t t_slot = tbase + lane_base + kColS + wg * 8;
         tmem_st8(t_slot, wh);
         tmem_st8(t_slot + 32, wl);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bar_aready[slot]);
+        mbar_arrive(&bar_aready);
       }
-      // ---------------- phase B: r = R - x -> pieces (32 features per thread) ----------------
+      // ---------------- phase B: r = (R_big + R_small) - x -> pieces (32 features per thread) ----------------
       {
         float4 xv[8];
 #pragma unroll
@@ -315,22 +320,29 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
         }
         BLK_WAIT(&bar_rfull, ti & 1u);
         tc_fence_after();
-        uint32_t rr[32];
-        tmem_ld32(tbase + lane_base + kColR + wg * 32, rr);
-        tmem_wait_ld();
-        uint32_t wh[16], wl[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 ra = bsub2(make_float2(__uint_as_float(rr[4 * j + 0]), __uint_as_float(rr[4 * j + 1])),
-                                  make_float2(xv[j].x, xv[j].y));
-          const float2 rc = bsub2(make_float2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])),
-                                  make_float2(xv[j].z, xv[j].w));
-          bsplit2(ra, wh[2 * j], wl[2 * j]);
-          bsplit2(rc, wh[2 * j + 1], wl[2 * j + 1]);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t rb[16], rs[16];
+          tmem_ld16(tbase + lane_base + kColR + wg * 32 + hf * 16, rb);
+          tmem_ld16(tbase + lane_base + kColRs + wg * 32 + hf * 16, rs);
+          tmem_wait_ld();
+          uint32_t wh[8], wl[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 xx = xv[hf * 4 + j];
+            const float2 ra = bsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 0]), __uint_as_float(rb[4 * j + 1])),
+                                               make_float2(__uint_as_float(rs[4 * j + 0]), __uint_as_float(rs[4 * j + 1]))),
+                                    make_float2(xx.x, xx.y));
+            const float2 rc = bsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3])),
+                                               make_float2(__uint_as_float(rs[4 * j + 2]), __uint_as_float(rs[4 * j + 3]))),
+                                    make_float2(xx.z, xx.w));
+            bsplit2(ra, wh[2 * j], wl[2 * j]);
+            bsplit2(rc, wh[2 * j + 1], wl[2 * j + 1]);
+          }
+          const uint32_t t_r = tbase + lane_base + kColRp + wg * 16 + hf * 8;
+          tmem_st8(t_r, wh);
+          tmem_st8(t_r + 64, wl);
         }
-        const uint32_t t_r = tbase + lane_base + kColRp + wg * 16;
-        tmem_st16(t_r, wh);
-        tmem_st16(t_r + 64, wl);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bar_rready);
@@ -481,7 +493,7 @@ typedef CUresult (*EncodeTiledFnB)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int blk_make_map(CUtensorMap* map, const float* base, int64_t rows, int cols) {
+int blk_make_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int tile_rows) {
   static EncodeTiledFnB fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
@@ -496,7 +508,7 @@ int blk_make_map(CUtensorMap* map, const float* base, int64_t rows, int cols) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)kTileM};
+  cuuint32_t box[2] = {32, (cuuint32_t)tile_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -568,9 +580,13 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
 
   CUtensorMap tm_a, tm_b;
   int rc;
-  if ((rc = blk_make_map(&tm_a, a.z_a, a.n, a.k))) return rc;
-  if ((rc = blk_make_map(&tm_b, a.z_b, a.n, a.k))) return rc;
-  const int64_t ntiles = (a.n + kTileM - 1) / kTileM;
+  // LASSO_B200_BLK_ROWS=64: half-height tiles (measured slower at C3, 1.47 vs 1.11 ms: the
+  // dictionary slices are re-streamed from L2 per tile, and that traffic doubles)
+  int trows = kTileM;
+  if (const char* t = getenv("LASSO_B200_BLK_ROWS")) trows = atoi(t) == 64 ? 64 : kTileM;
+  if ((rc = blk_make_map(&tm_a, a.z_a, a.n, a.k, trows))) return rc;
+  if ((rc = blk_make_map(&tm_b, a.z_b, a.n, a.k, trows))) return rc;
+  const int64_t ntiles = (a.n + trows - 1) / trows;
   const unsigned grid = (unsigned)(ntiles < S.num_sms ? ntiles : S.num_sms);
   double t = 1.0;
   for (int it = 0; it < a.maxiter; ++it) {
@@ -591,6 +607,7 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
     }
     p.beta = (float)beta;
     p.use_prev = it > 0 ? 1 : 0;
+    p.trows = trows;
     p.scal = S.scal;
     p.ctl.hist = a.hist;
     p.ctl.tol_abs = a.tol_abs;
