@@ -619,7 +619,8 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
     count_launch();
   }
   // both buffers go back to the caller's units (the stop test may select either one)
-  const float limit = 32768.0f;
+  float limit = 32768.0f;
+  if (const char* lim = getenv("LASSO_B200_RES_LIMIT")) limit = (float)atof(lim);   // tests: force the fallback
   const int blocks = (int)std::min<int64_t>((a.n + 7) / 8, (int64_t)S.num_sms * 16);
   blk_unscale_kernel<<<blocks, 256, 0, st>>>(a.z_a, a.n, a.k, S.row_scale, S.scal, limit, S.flag);
   LASSO_CHECK_LAUNCH();

@@ -151,13 +151,64 @@ def test_auto_takes_the_resident_kernel(dev):
     assert _cabi.select_path(65536, 64, 256) == _cabi.PATH_RESIDENT
     assert _cabi.select_path(128, 10, 50) == _cabi.PATH_RESIDENT    # unaligned rows are fine
     assert _cabi.select_path(128, 65, 50) == _cabi.PATH_FFMA        # d > 64
-    assert _cabi.select_path(1000, 128, 1024) == _cabi.PATH_FFMA    # C3: dictionary exceeds one SM
+    assert _cabi.select_path(1000, 128, 1024) == _cabi.PATH_BLOCKED  # C3: dictionary exceeds one SM
+    assert _cabi.select_path(1000, 150, 90) == _cabi.PATH_FFMA
+
+
+@pytest.mark.parametrize("n,d,k,kind,alpha,iters", [
+    (300, 128, 1024, "planted", 0.05, 40),      # BASELINE config 3 shape
+    (200, 128, 1024, "randn", 0.05, 30),
+    (1000, 64, 512, "planted", 0.1, 25),        # the conv2d config's im2col shape (64-dim patches, 512 filters)
+    (130, 100, 300, "randn", 0.1, 20),          # ragged: last chunk and feature block partly empty
+    (257, 72, 320, "planted", 0.1, 1),
+])
+def test_blocked_kernel_matches_oracle(dev, n, d, k, kind, alpha, iters):
+    assert _cabi.select_path(n, d, k) == _cabi.PATH_BLOCKED
+    fallbacks = _cabi.resident_fallbacks()
+    x, w = make_problem(n, d, k, seed=0, kind=kind)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    got = sparse_encode(x.to(dev), w.to(dev), alpha=alpha, lr=lr, maxiter=iters, tol=0.0)     # auto
+    want = oracle.ista(x, torch.zeros(n, k), w, alpha=alpha, lr=lr, maxiter=iters, tol=0.0)
+    assert rel_fro(got, want) <= TOL
+    assert support_mismatch(got.cpu(), want) <= 2e-3
+    assert _cabi.resident_fallbacks() == fallbacks      # solved by the tensor-core kernel itself
+
+
+def test_blocked_kernel_warm_start_stop_test_and_fallback(dev, monkeypatch):
+    n, d, k = 400, 128, 768
+    x, w = make_problem(n, d, k, seed=3)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    xd, wd = x.to(dev), w.to(dev)
+    g = torch.Generator().manual_seed(5)
+    z0 = 0.05 * torch.randn(n, k, generator=g)
+    for fast in (True, False):
+        got, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 20, fast, -1.0, path="blocked")
+        want = oracle.ista(x, z0, w, alpha=0.1, fast=fast, lr=lr, maxiter=20, tol=0.0)
+        assert rel_fro(got, want) <= TOL
+    # batch-global stop test, evaluated on the device between launches: same count and history as FFMA
+    tol_abs = float(np.float32(n * k * 1e-3))
+    zb, it_b, hb = _cabi.fista_device(xd, wd, None, 0.1, lr, 400, True, tol_abs, path="blocked",
+                                      want_iters=True, want_hist=True)
+    zf, it_f, hf = _cabi.fista_device(xd, wd, None, 0.1, lr, 400, True, tol_abs, path="ffma",
+                                      want_iters=True, want_hist=True)
+    assert 1 < it_b < 400 and it_b == it_f and rel_fro(zb, zf) <= TOL
+    np.testing.assert_allclose(hb.cpu().numpy()[:it_b - 1], hf.cpu().numpy()[:it_b - 1], rtol=1e-4)
+    # in place over the start buffer, and the hand-over to the FFMA kernel from the intact start
+    before = _cabi.resident_fallbacks()
+    monkeypatch.setenv("LASSO_B200_RES_LIMIT", "1e-3")
+    buf = z0.to(dev).clone()
+    got, _, _ = _cabi.fista_device(xd, wd, buf, 0.1, lr, 9, True, -1.0, path="blocked", out=buf)
+    monkeypatch.delenv("LASSO_B200_RES_LIMIT")
+    assert _cabi.resident_fallbacks() == before + 1
+    ffma, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 9, True, -1.0, path="ffma")
+    assert torch.equal(got, ffma)
 
 
 def test_resident_rows_at_wildly_different_scales(dev):
     # every row is its own lasso problem and is rescaled on its own: the relative error of EACH
     # row stays at the float32 level although the batch spans 12 orders of magnitude
     n, d, k, iters = 600, 64, 256, 60
+    fallbacks = _cabi.resident_fallbacks()
     x, w = make_problem(n, d, k, seed=5, kind="planted")
     g = torch.Generator().manual_seed(11)
     scale = 10.0 ** (12 * torch.rand(n, 1, generator=g) - 6)
@@ -182,7 +233,7 @@ def test_resident_rows_at_wildly_different_scales(dev):
     row_err = (gotm - wantm).double().norm(dim=1)[live] / wantm.double().norm(dim=1)[live]
     assert float(row_err.max()) <= TOL
     assert float(gotm[~live].abs().max() if (~live).any() else 0.0) == 0.0
-    assert _cabi.resident_fallbacks() == 0
+    assert _cabi.resident_fallbacks() == fallbacks
 
 
 def test_resident_falls_back_to_the_streaming_kernel(dev, monkeypatch):
