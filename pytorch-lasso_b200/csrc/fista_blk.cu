@@ -73,6 +73,7 @@ struct BlkParams {
   float beta;
   int use_prev;
   int trows;                // rows per tile: 128 (64 for experiments: half of the MMA rows idle)
+  int l2_hints;             // TMA cache hints (LASSO_B200_BLK_L2=1 enables)
   const BlkScalars* scal;
   StepCtl ctl;
   volatile int* dbg;
@@ -182,10 +183,14 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
           if (elect_one()) {
             uint8_t* st = smem + s * kStageBytes;
             mbar_expect_tx(&bar_full[s], 4u * box_bytes + kWSliceBytes);
-            tma_load_2d(st, &tm_cur, q * kQ, row0, &bar_full[s]);
-            tma_load_2d(st + kBoxBytes, &tm_cur, q * kQ + 32, row0, &bar_full[s]);
-            tma_load_2d(st + kZChunkBytes, &tm_prev, q * kQ, row0, &bar_full[s]);
-            tma_load_2d(st + kZChunkBytes + kBoxBytes, &tm_prev, q * kQ + 32, row0, &bar_full[s]);
+            // L2 priorities: z_cur of pass 1 is read again ~40 us later in pass 2 -> keep it; the
+            // rest is touched for the last time in this launch -> first to go
+            const uint64_t pol_cur = (pass == 0 && p.l2_hints) ? kEvictLast : (p.l2_hints ? kEvictFirst : kEvictNormal);
+            const uint64_t pol_prev = p.l2_hints ? kEvictFirst : kEvictNormal;
+            tma_load_2d_hint(st, &tm_cur, q * kQ, row0, &bar_full[s], pol_cur);
+            tma_load_2d_hint(st + kBoxBytes, &tm_cur, q * kQ + 32, row0, &bar_full[s], pol_cur);
+            tma_load_2d_hint(st + kZChunkBytes, &tm_prev, q * kQ, row0, &bar_full[s], pol_prev);
+            tma_load_2d_hint(st + kZChunkBytes + kBoxBytes, &tm_prev, q * kQ + 32, row0, &bar_full[s], pol_prev);
             bulk_load(st + 2 * kZChunkBytes, p.w_image + (size_t)q * kWSliceBytes, 16384, &bar_full[s]);
             bulk_load(st + 2 * kZChunkBytes + 16384, p.w_image + (size_t)q * kWSliceBytes + 16384, 16384, &bar_full[s]);
           }
@@ -584,6 +589,10 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
   // dictionary slices are re-streamed from L2 per tile, and that traffic doubles)
   int trows = kTileM;
   if (const char* t = getenv("LASSO_B200_BLK_ROWS")) trows = atoi(t) == 64 ? 64 : kTileM;
+  // LASSO_B200_BLK_L2=1: evict-last on pass 1's z_cur, evict-first elsewhere.  Measured at C3: no
+  // gain (1.070 vs 1.056 ms) -- 148 tiles x 1 MB in flight exceed the L2 either way
+  int l2_hints = 0;
+  if (const char* t = getenv("LASSO_B200_BLK_L2")) l2_hints = atoi(t) != 0;
   if ((rc = blk_make_map(&tm_a, a.z_a, a.n, a.k, trows))) return rc;
   if ((rc = blk_make_map(&tm_b, a.z_b, a.n, a.k, trows))) return rc;
   const int64_t ntiles = (a.n + trows - 1) / trows;
@@ -608,6 +617,7 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
     p.beta = (float)beta;
     p.use_prev = it > 0 ? 1 : 0;
     p.trows = trows;
+    p.l2_hints = l2_hints;
     p.scal = S.scal;
     p.ctl.hist = a.hist;
     p.ctl.tol_abs = a.tol_abs;
