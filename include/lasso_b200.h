@@ -111,6 +111,27 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
                                   int32_t path);
 
 /*
+ * Convolutional ISTA / FISTA -- replaces the loop of lasso/conv2d/ista.py:7-49 (stride 1,
+ * padding 0) as im2col -> linear: rows are the oh x ow patches of every image
+ * (oh = h - kh + 1, ow = w - kw + 1), features the cin*kh*kw patch entries, atoms the filters.
+ *   conv_transpose2d(z, W) = fold(Z weight_lin^T)   (ista.py:18)
+ *   conv2d(r, W)           = unfold(r) weight_lin    (ista.py:19)
+ * so every iteration is the first half of the k-blocked tcgen05 kernel (R = Y weight_lin^T),
+ * the residual in image space (overlap-add of the patches, minus x, re-unfolded) and its
+ * second half (gradient, soft threshold, momentum).
+ *   x            device [n_img, cin, h, w]
+ *   weight_lin   device [cin*kh*kw, k]: weight_lin[c*kh*kw + a*kw + b, f] = W[f, c, a, b]
+ *   z0, z_out    device [n_img*oh*ow, k] (codes in patch-major "NHWC" order; z0 may be NULL)
+ * Limits: cin*kh*kw <= 128 and k <= 1024 (multiples of 4), one image's patch matrix <= 200 KB.
+ * Other arguments as lasso_b200_fista_f32.  Synchronises the stream once.
+ */
+int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, const float* z0,
+                                    float* z_out, int64_t n_img, int32_t cin, int32_t h, int32_t w,
+                                    int32_t kh, int32_t kw, int32_t k, double alpha, double lr,
+                                    int32_t maxiter, int32_t fast, double tol_abs,
+                                    int32_t* iters_done, double* delta_hist, void* stream);
+
+/*
  * Lipschitz constant L = lambda_max(W^T W) -- replaces _lipschitz_constant,
  * ista.py:8-14 (Gram + D2H + ARPACK eigsh) by an on-device float64 power
  * iteration on the smaller Gram.  Synchronises; result in *l_out (host).

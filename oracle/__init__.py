@@ -12,6 +12,7 @@ the build container by ``tests/golden/make_golden.py`` and committed under
 """
 from .ista_oracle import (  # noqa: F401
     beta_schedule,
+    conv2d_ista,
     dict_learning,
     initialize_code,
     ista,

@@ -292,3 +292,37 @@ def dict_learning(x, n_components, alpha=1.0, constrained=True, persist=False,
         else:
             weight = update_dict_ridge(x, z, lambd=lambd)
     return weight, losses
+
+
+# --------------------------------------------------------------------------
+# convolutional ISTA / FISTA  (lasso/conv2d/ista.py:7-49)
+# --------------------------------------------------------------------------
+
+def conv2d_ista(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True, maxiter=10, lr=None,
+                tol=1e-5, return_iters=False):
+    """Restatement of ``ista_conv2d`` with the reference's torch calls in the reference's order:
+    the decoder is ``conv_transpose2d`` (ista.py:18), its adjoint ``conv2d`` (ista.py:19), the
+    momentum update comes BEFORE the stop test (ista.py:40-47).  ``lr`` must be a float here
+    (the 'auto' bound is checked separately against the reference)."""
+    thresh = z0.numel() * tol                                     # ista.py:16
+
+    def grad(code):
+        recon = F.conv_transpose2d(code, weight, stride=stride, padding=padding)
+        return F.conv2d(recon - x, weight, stride=stride, padding=padding)
+
+    z = z0
+    point, t = z0, 1
+    done = 0
+    for _ in range(maxiter):
+        done += 1
+        base = point if fast else z
+        z_next = F.softshrink(base - lr * grad(base), alpha * lr)   # ista.py:27-28
+        if fast:
+            t_next = (1 + math.sqrt(1 + 4 * t ** 2)) / 2
+            point = z_next + ((t - 1) / t_next) * (z_next - z)
+            t = t_next
+        if (z - z_next).abs().sum() <= thresh:
+            z = z_next
+            break
+        z = z_next
+    return (z, done) if return_iters else z

@@ -10,6 +10,7 @@ arithmetic runs in ``csrc/liblasso_b200.so`` behind the C ABI declared in
 """
 from . import _cabi  # noqa: F401
 from . import linear  # noqa: F401
+from . import conv2d  # noqa: F401
 from . import testing  # noqa: F401
 from ._cabi import LassoB200Error  # noqa: F401
 

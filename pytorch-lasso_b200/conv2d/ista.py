@@ -1,0 +1,59 @@
+"""Convolutional ISTA / FISTA -- mirrors ``lasso.conv2d.ista.ista_conv2d`` (lasso/conv2d/ista.py:7-49).
+
+Same signature, defaults and error behaviour.  The loop runs in ``liblasso_b200.so`` as
+im2col -> linear on the k-blocked tcgen05 kernel (``lasso_b200_conv2d_fista_f32``):
+``conv_transpose2d(z, W)`` is the overlap-add of ``Z W_lin^T`` and ``conv2d(r, W)`` is
+``unfold(r) W_lin``, with the residual formed in image space between the two halves of an
+iteration.  Codes keep the reference's layout ``[n, filters, oh, ow]`` at the boundary; inside
+they are patch-major rows ``[n*oh*ow, filters]`` (two permutes per call).
+
+Built: ``stride=1``, ``padding=0``, ``cin*kh*kw <= 128``, ``filters <= 1024`` (multiples of 4).
+Everything else raises -- there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from ..linear import utils as _utils
+from .lip_const import lip_bound_conv2d
+
+__all__ = ["ista_conv2d"]
+
+
+def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
+                maxiter=10, lr='auto', tol=1e-5, verbose=False):
+    if lr == 'auto':
+        if stride != 1:
+            raise NotImplementedError("auto lr is only implemented for "
+                                      "stride == 1.")          # ista.py:10-12
+        lr = 1 / float(lip_bound_conv2d(weight, padding))      # ista.py:13-15 (odd kernels only)
+    if stride != 1 or padding != 0:
+        raise NotImplementedError("lasso_b200.conv2d is built for stride=1, padding=0")
+    if verbose:
+        raise NotImplementedError("verbose=True is not built for the convolutional path")
+    for name, t in (("x", x), ("z0", z0), ("weight", weight)):
+        if t.dtype != torch.float32:
+            raise NotImplementedError("lasso_b200 computes in float32 only; {} has dtype {}".format(name, t.dtype))
+        if t.requires_grad:
+            raise NotImplementedError("lasso_b200 does not record an autograd graph; detach {} first".format(name))
+    if maxiter == 0:
+        return z0
+    filters, cin, kh, kw = weight.shape
+    n, cx, h, w = x.shape
+    oh, ow = h - kh + 1, w - kw + 1
+    if cx != cin or tuple(z0.shape) != (n, filters, oh, ow):
+        raise ValueError("expected x[n,{},h,w] and z0[n,{},{},{}]; got {} and {}".format(
+            cin, filters, oh, ow, tuple(x.shape), tuple(z0.shape)))
+    dev = x.device if x.is_cuda else _utils.default_device()
+    tol_abs = float(np.float32(z0.numel() * tol))              # ista.py:16
+    # weight_lin[c*kh*kw + a*kw + b, f] = W[f, c, a, b];  codes as patch-major rows
+    w_lin = weight.to(dev).reshape(filters, cin * kh * kw).T.contiguous()
+    z_rows = z0.to(dev).permute(0, 2, 3, 1).reshape(n * oh * ow, filters).contiguous()
+    if not bool(z_rows.any()):
+        z_rows = None                                          # zero start: the kernel clears its own buffer
+    out_rows, _ = _cabi.conv2d_fista_device(x.to(dev).contiguous(), w_lin, z_rows, kh, kw, alpha, float(lr),
+                                            maxiter, fast, tol_abs)
+    z = out_rows.reshape(n, oh, ow, filters).permute(0, 3, 1, 2).contiguous()
+    return z if x.is_cuda else z.cpu()

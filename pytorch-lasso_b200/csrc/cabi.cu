@@ -316,6 +316,97 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   return LASSO_B200_OK;
 }
 
+
+int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, const float* z0, float* z_out,
+                                    int64_t n_img, int32_t cin, int32_t h, int32_t w, int32_t kh, int32_t kw,
+                                    int32_t k, double alpha, double lr, int32_t maxiter, int32_t fast,
+                                    double tol_abs, int32_t* iters_done, double* delta_hist, void* stream) {
+  t_error[0] = 0;
+  if (n_img < 0 || cin <= 0 || kh <= 0 || kw <= 0 || h < kh || w < kw || k <= 0 || !weight_lin ||
+      (n_img > 0 && (!x || !z_out))) {
+    set_error("invalid argument to conv2d_fista");
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (maxiter < 0 || !(lr > 0.0) || !std::isfinite(lr) || !std::isfinite(alpha)) {
+    set_error("invalid maxiter=%d / lr=%g / alpha=%g", maxiter, lr, alpha);
+    return LASSO_B200_ERR_INVALID;
+  }
+  if (n_img == 0) {
+    if (iters_done) *iters_done = 0;
+    return LASSO_B200_OK;
+  }
+  const int64_t P = (int64_t)(h - kh + 1) * (w - kw + 1), n = n_img * P;
+  const int d = cin * kh * kw;
+  if (!conv2d_blk_supported(n_img, cin, h, w, kh, kw, k)) {
+    set_error("conv2d path needs cin*kh*kw <= 128 (multiple of 4), filters <= 1024 (multiple of 4) and one image's "
+              "patch matrix within 200 KB; got cin=%d %dx%d kernel, %d filters, %dx%d images", cin, kh, kw, k, h, w);
+    return LASSO_B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t code_bytes = sizeof(float) * (size_t)n * (size_t)k;
+  if (maxiter == 0) {
+    if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_out, 0, code_bytes, st));
+    else if (z0 != z_out) LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
+    if (iters_done) *iters_done = 0;
+    return LASSO_B200_OK;
+  }
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  Workspace* ws = nullptr;
+  int rc = current_workspace(&ws);
+  if (rc) return rc;
+  if ((rc = ensure(ws->code, code_bytes))) return rc;
+  if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
+  if ((rc = ensure(ws->ctl, 256))) return rc;
+  double* hist = (double*)ws->hist.ptr;
+  float* wsbuf = (float*)ws->code.ptr;
+  float* z_a = (maxiter & 1) ? wsbuf : z_out;   // z_i lives in (i even ? z_a : z_b)
+  float* z_b = (maxiter & 1) ? z_out : wsbuf;
+  if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(z_a, 0, code_bytes, st));
+  else if (z0 != z_a) LASSO_CUDA_TRY(cudaMemcpyAsync(z_a, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
+  LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+  FistaArgs a{};
+  a.x = x;
+  a.w = weight_lin;
+  a.z_a = z_a;
+  a.z_b = z_b;
+  a.n = n;
+  a.d = d;
+  a.k = k;
+  a.lr = (float)lr;
+  a.lam = (float)(alpha * lr);
+  a.maxiter = maxiter;
+  a.fast = fast ? 1 : 0;
+  a.tol_abs = tol_abs;
+  a.hist = hist;
+  ConvShape shape{n_img, cin, h, w, kh, kw};
+  int fell_back = 0;
+  if ((rc = fista_blk_run(a, &fell_back, st, &shape))) return rc;
+  if (fell_back) {
+    set_error("conv2d_fista: an iterate left the fp16 operand range of the tensor-core kernel (non-finite input, or "
+              "codes more than 2^9 times larger than the per-image scaling allows); there is no CUDA-core conv path");
+    return LASSO_B200_ERR_UNSUPPORTED;
+  }
+  int* ctl = (int*)ws->ctl.ptr;
+  find_stop_kernel<<<1, 256, 0, st>>>(hist, maxiter, tol_abs, ctl);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  if (tol_abs >= 0.0) {
+    int blocks = (int)std::min<int64_t>(((int64_t)n * k + 1023) / 1024, 148 * 8);
+    select_result_kernel<<<blocks, 256, 0, st>>>(z_a, z_b, z_out, (int64_t)n * k, ctl);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+  }
+  if (delta_hist)
+    LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, hist, sizeof(double) * (size_t)maxiter, cudaMemcpyDeviceToDevice, st));
+  if (iters_done) {
+    int done = 0;
+    LASSO_CUDA_TRY(cudaMemcpyAsync(&done, ctl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+    *iters_done = done;
+  }
+  return LASSO_B200_OK;
+}
+
 }  // extern "C" (reopened below)
 
 namespace lasso {

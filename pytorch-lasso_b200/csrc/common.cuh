@@ -108,8 +108,13 @@ struct ResScalars {
 };
 
 int fista_ffma_run(const FistaArgs& a, float* z_out, cudaStream_t st);
+struct ConvShape {
+  int64_t n_img;
+  int cin, h, w, kh, kw;
+};
 bool fista_blk_supported(int64_t n, int d, int k);
-int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st);
+bool conv2d_blk_supported(int64_t n_img, int cin, int h, int w, int kh, int kw, int k);
+int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const ConvShape* conv = nullptr);
 bool fista_res_supported(int64_t n, int d, int k);
 int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int iters, int fast,
                       cudaStream_t st);

@@ -74,6 +74,10 @@ struct BlkParams {
   int use_prev;
   int trows;                // rows per tile: 128 (64 for experiments: half of the MMA rows idle)
   int l2_hints;             // TMA cache hints (LASSO_B200_BLK_L2=1 enables)
+  int mode;                 // 0: whole iteration.  Convolutional lasso (patches of an image overlap, so
+                            // the residual is formed in image space by conv_resid_kernel between the
+                            // two halves): 1 = pass 1 only, R -> r_buf;  2 = r <- r_buf, pass 2 only
+  float* r_buf;             // [n][d] (modes 1, 2)
   const BlkScalars* scal;
   StepCtl ctl;
   volatile int* dbg;
@@ -177,6 +181,7 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
       const int row0 = ((int)blockIdx.x + tile * (int)gridDim.x) * trows;
       const uint32_t box_bytes = (uint32_t)trows * 128u;
       for (int pass = 0; pass < 2; ++pass) {
+        if ((pass == 0 && p.mode == 2) || (pass == 1 && p.mode == 1)) continue;
         for (int q = 0; q < nq; ++q, ++cc) {
           const uint32_t s = cc & 1u, ph = (cc >> 1) & 1u;
           BLK_WAIT(&bar_empty[s], ph ^ 1u);
@@ -206,7 +211,7 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
     uint32_t cc = 0, pc = 0, gc = 0, ti = 0;   // chunk loads / piece chunks / G chunks / tiles seen
     for (int tile = 0; tile < my_tiles; ++tile, ++ti) {
       // ---- pass 1: GEMM1 slices ----
-      for (int q = 0; q < nq; ++q, ++cc, ++pc) {
+      for (int q = 0; q < (p.mode == 2 ? 0 : nq); ++q, ++cc, ++pc) {
         const uint32_t s = cc & 1u;
         BLK_WAIT(&bar_full[s], (cc >> 1) & 1u);       // dictionary slice landed
         BLK_WAIT(&bar_aready, pc & 1u);               // pieces of y_q staged
@@ -232,9 +237,9 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
         __syncwarp();
       }
       // ---- pass 2: GEMM2 chunks ----
-      BLK_WAIT(&bar_rready, ti & 1u);
+      BLK_WAIT(&bar_rready, ti & 1u);   // (mode 1: R has been read, the next tile may overwrite it)
       tc_fence_after();
-      for (int q = 0; q < nq; ++q, ++cc, ++gc) {
+      for (int q = 0; q < (p.mode == 1 ? 0 : nq); ++q, ++cc, ++gc) {
         const uint32_t s = cc & 1u;
         BLK_WAIT(&bar_full[s], (cc >> 1) & 1u);
         if (gc > 0) BLK_WAIT(&bar_gfree, (gc - 1) & 1u);   // the single G buffer has been drained
@@ -282,7 +287,7 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
       const float lam = sc.lam * sxr;
       const float uz_row = sc.sw / sxr;
       // ---------------- pass 1: y chunks -> pieces ----------------
-      for (int q = 0; q < nq; ++q, ++cc, ++pc) {
+      for (int q = 0; q < (p.mode == 2 ? 0 : nq); ++q, ++cc, ++pc) {
         const uint32_t s = cc & 1u;
         BLK_WAIT(&bar_full[s], (cc >> 1) & 1u);
         const uint8_t* zc_s = smem + s * kStageBytes + zbox;
@@ -312,13 +317,38 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
         mbar_arrive(&bar_aready);
       }
       // ---------------- phase B: r = (R_big + R_small) - x -> pieces (32 features per thread) ----------------
-      {
+      if (p.mode == 2) {
+        // the residual comes from conv_resid_kernel (image space), already in scaled units
+        float4 rv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = wg * 32 + 4 * j;
+          rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && col < p.d) rv[j] = __ldg(reinterpret_cast<const float4*>(p.r_buf + grow * p.d + col));
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t wh[8], wl[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 rr = rv[hf * 4 + j];
+            bsplit2(make_float2(rr.x, rr.y), wh[2 * j], wl[2 * j]);
+            bsplit2(make_float2(rr.z, rr.w), wh[2 * j + 1], wl[2 * j + 1]);
+          }
+          const uint32_t t_r = tbase + lane_base + kColRp + wg * 16 + hf * 8;
+          tmem_st8(t_r, wh);
+          tmem_st8(t_r + 64, wl);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bar_rready);
+      } else {
         float4 xv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int col = wg * 32 + 4 * j;
           xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok && col < p.d) {
+          if (p.mode == 0 && row_ok && col < p.d) {
             xv[j] = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.d + col));
             xv[j].x *= sxr; xv[j].y *= sxr; xv[j].z *= sxr; xv[j].w *= sxr;
           }
@@ -341,12 +371,21 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
             const float2 rc = bsub2(__fadd2_rn(make_float2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3])),
                                                make_float2(__uint_as_float(rs[4 * j + 2]), __uint_as_float(rs[4 * j + 3]))),
                                     make_float2(xx.z, xx.w));
-            bsplit2(ra, wh[2 * j], wl[2 * j]);
-            bsplit2(rc, wh[2 * j + 1], wl[2 * j + 1]);
+            if (p.mode == 1) {
+              // R = Y W^T (scaled units) goes to HBM: the overlap-add happens in image space
+              const int col = wg * 32 + hf * 16 + 4 * j;
+              if (row_ok && col < p.d)
+                *reinterpret_cast<float4*>(p.r_buf + grow * p.d + col) = make_float4(ra.x, ra.y, rc.x, rc.y);
+            } else {
+              bsplit2(ra, wh[2 * j], wl[2 * j]);
+              bsplit2(rc, wh[2 * j + 1], wl[2 * j + 1]);
+            }
           }
-          const uint32_t t_r = tbase + lane_base + kColRp + wg * 16 + hf * 8;
-          tmem_st8(t_r, wh);
-          tmem_st8(t_r + 64, wl);
+          if (p.mode == 0) {
+            const uint32_t t_r = tbase + lane_base + kColRp + wg * 16 + hf * 8;
+            tmem_st8(t_r, wh);
+            tmem_st8(t_r + 64, wl);
+          }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -354,7 +393,7 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
       }
       // ---------------- pass 2: fused update, z+ over z_prev in HBM ----------------
       float part = 0.f;
-      for (int q = 0; q < nq; ++q, ++cc, ++gc) {
+      for (int q = 0; q < (p.mode == 1 ? 0 : nq); ++q, ++cc, ++gc) {
         const uint32_t s = cc & 1u;
         BLK_WAIT(&bar_full[s], (cc >> 1) & 1u);
         const uint8_t* zc_s = smem + s * kStageBytes + zbox;
@@ -402,7 +441,7 @@ fista_blk_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_consta
       }
       if (row_ok) dsum += (double)(part * uz_row);
     }
-    if (p.ctl.hist != nullptr) {
+    if (p.ctl.hist != nullptr && p.mode != 1) {
       dsum = warp_sum(dsum);
       if (lane == 0 && dsum != 0.0) atomicAdd(&p.ctl.hist[p.ctl.iter], dsum);
     }
@@ -494,6 +533,87 @@ __global__ void blk_unscale_kernel(float* __restrict__ z, int64_t n, int k, cons
   if (bad) atomicExch(flag, 1);
 }
 
+
+// ---- convolutional lasso (lasso/conv2d/ista.py:7-49) as im2col -> linear ---------------------
+// rows = the oh x ow patches of every image, features = cin x kh x kw, atoms = filters:
+//   conv_transpose2d(z, W) = fold(Z W_lin^T),  conv2d(r, W) = unfold(r) W_lin  (stride 1, no padding)
+// so an iteration is pass 1 (R = Y W_lin^T, mode 1), the residual in IMAGE space
+// r = unfold(fold(R) - x) -- patches overlap, rows are coupled inside an image -- and pass 2 (mode 2).
+
+// per-image power-of-two scale (all patch rows of an image share it): one CTA per image
+__global__ void __launch_bounds__(256) conv_scale_kernel(const float* __restrict__ x, int img_elems, int P, int k,
+                                                         const BlkScalars* __restrict__ sc,
+                                                         float* __restrict__ row_scale, float* __restrict__ z_a,
+                                                         int scale_z) {
+  __shared__ float red[8];
+  __shared__ float s_sx;
+  const int64_t img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = 0.f;
+  for (int i = tid; i < img_elems; i += blockDim.x) m = fmaxf(m, fabsf(x[img * img_elems + i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float mm = 0.f;
+    for (int i = 0; i < 8; ++i) mm = fmaxf(mm, red[i]);
+    float sxr = 1.f;
+    if (mm > 0.f && mm < 3.0e38f) {
+      const int be = 260 - (int)((__float_as_uint(mm) >> 23) & 0xFFu);
+      sxr = __uint_as_float((uint32_t)min(max(be, 1), 254) << 23);
+    }
+    s_sx = sxr;
+  }
+  __syncthreads();
+  const float sxr = s_sx;
+  for (int pch = tid; pch < P; pch += blockDim.x) row_scale[img * P + pch] = sxr;
+  if (scale_z) {
+    const float szr = sxr * sc->isw;
+    float* zi = z_a + img * (int64_t)P * k;
+    for (int64_t i = tid; i < (int64_t)P * k; i += blockDim.x) zi[i] *= szr;
+  }
+}
+
+// r = unfold(fold(R) - sx x), in place on the [P][d] block of one image; one CTA per image
+__global__ void __launch_bounds__(512) conv_resid_kernel(float* __restrict__ rbuf, const float* __restrict__ x,
+                                                         const float* __restrict__ row_scale, int cin, int H, int W,
+                                                         int kh, int kw, StepCtl ctl) {
+  extern __shared__ __align__(16) float conv_smem[];
+  if (ctl.tol_abs >= 0.0 && ctl.iter >= 1 && ctl.hist[ctl.iter - 1] <= ctl.tol_abs) return;
+  const int oh = H - kh + 1, ow = W - kw + 1, P = oh * ow, kk = kh * kw, d = cin * kk;
+  float* Rs = conv_smem;              // [P][d]
+  float* img = conv_smem + P * d;     // [cin][H][W]
+  const int64_t i_img = blockIdx.x;
+  float* rb = rbuf + i_img * (int64_t)P * d;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < (P * d) / 4; e += blockDim.x)
+    reinterpret_cast<float4*>(Rs)[e] = reinterpret_cast<const float4*>(rb)[e];
+  const float sx = row_scale[i_img * P];
+  __syncthreads();
+  for (int pix = tid; pix < cin * H * W; pix += blockDim.x) {
+    const int c = pix / (H * W), i = (pix / W) % H, j = pix % W;
+    float acc = 0.f;
+    for (int a = 0; a < kh; ++a) {
+      const int pi = i - a;
+      if (pi < 0 || pi >= oh) continue;
+      for (int b = 0; b < kw; ++b) {
+        const int pj = j - b;
+        if (pj < 0 || pj >= ow) continue;
+        acc += Rs[(pi * ow + pj) * d + c * kk + a * kw + b];
+      }
+    }
+    img[pix] = acc - sx * x[i_img * (int64_t)(cin * H * W) + pix];
+  }
+  __syncthreads();
+  for (int e = tid; e < P * d; e += blockDim.x) {
+    const int pch = e / d, f = e % d;
+    const int c = f / kk, a = (f / kw) % kh, b = f % kw;
+    const int pi = pch / ow, pj = pch % ow;
+    rb[e] = img[c * H * W + (pi + a) * W + pj + b];
+  }
+}
+
 typedef CUresult (*EncodeTiledFnB)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -531,6 +651,9 @@ struct BlkState {
   int* flag = nullptr;
   float* row_scale = nullptr;
   int64_t row_cap = 0;
+  float* r_buf = nullptr;     // [rows][d] residual of the convolutional path
+  size_t r_cap = 0;
+  bool conv_attr_set = false;
   int num_sms = 0;
   bool attr_set = false;
   int* dbg_host = nullptr;
@@ -545,9 +668,18 @@ bool fista_blk_supported(int64_t n, int d, int k) {
          n < ((int64_t)1 << 31) - kTileM;
 }
 
+bool conv2d_blk_supported(int64_t n_img, int cin, int h, int w, int kh, int kw, int k) {
+  if (n_img < 1 || cin < 1 || kh < 1 || kw < 1 || h < kh || w < kw) return false;
+  const int64_t P = (int64_t)(h - kh + 1) * (w - kw + 1);
+  const int d = cin * kh * kw;
+  return fista_blk_supported(n_img * P, d, k) && (size_t)(P * d + (int64_t)cin * h * w) * sizeof(float) <= 200 * 1024;
+}
+
 // Same contract as fista_tc_run: z_i lives in (i even ? z_a : z_b).  *fell_back = 1 when an
 // iterate left the fp16 operand range (the buffers are then unspecified).  Synchronises the stream.
-int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
+// conv != nullptr: a.x is the image batch [n_img][cin][h][w], rows are its patches (a.n = n_img * P,
+// a.d = cin * kh * kw) and every iteration is pass 1, conv_resid_kernel, pass 2.
+int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const ConvShape* conv) {
   int dev = 0;
   LASSO_CUDA_TRY(cudaGetDevice(&dev));
   BlkState& S = g_blk[dev];
@@ -579,7 +711,29 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
   LASSO_CHECK_LAUNCH();
   blk_prep_w_kernel<<<(kDPB * nq * kQ + 255) / 256, 256, 0, st>>>(a.w, a.d, a.k, nq, S.scal, S.w_image);
   LASSO_CHECK_LAUNCH();
-  blk_rowscale_kernel<<<(unsigned)((a.n + 7) / 8), 256, 0, st>>>(a.x, a.n, a.d, a.k, S.scal, S.row_scale, a.z_a, 1);
+  int conv_P = 0;
+  size_t conv_smem = 0;
+  if (conv) {
+    conv_P = (conv->h - conv->kh + 1) * (conv->w - conv->kw + 1);
+    conv_smem = ((size_t)conv_P * a.d + (size_t)conv->cin * conv->h * conv->w) * sizeof(float);
+    const size_t need = sizeof(float) * (size_t)a.n * a.d;
+    if (need > S.r_cap) {
+      if (S.r_buf) LASSO_CUDA_TRY(cudaFree(S.r_buf));
+      S.r_buf = nullptr;
+      S.r_cap = 0;
+      LASSO_CUDA_TRY(cudaMalloc(&S.r_buf, need));
+      S.r_cap = need;
+    }
+    if (!S.conv_attr_set) {
+      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)conv_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+      S.conv_attr_set = true;
+    }
+    conv_scale_kernel<<<(unsigned)conv->n_img, 256, 0, st>>>(a.x, conv->cin * conv->h * conv->w, conv_P, a.k, S.scal,
+                                                             S.row_scale, a.z_a, 1);
+  } else {
+    blk_rowscale_kernel<<<(unsigned)((a.n + 7) / 8), 256, 0, st>>>(a.x, a.n, a.d, a.k, S.scal, S.row_scale, a.z_a, 1);
+  }
   LASSO_CHECK_LAUNCH();
   count_launch(3);
 
@@ -623,10 +777,20 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
     p.ctl.tol_abs = a.tol_abs;
     p.ctl.iter = it;
     p.dbg = S.dbg_dev;
-    if (it & 1) fista_blk_kernel<<<grid, kThreadsB, kSmemBytesB, st>>>(tm_b, tm_a, p);
-    else fista_blk_kernel<<<grid, kThreadsB, kSmemBytesB, st>>>(tm_a, tm_b, p);
-    LASSO_CHECK_LAUNCH();
-    count_launch();
+    p.r_buf = S.r_buf;
+    for (int half = 0; half < (conv ? 2 : 1); ++half) {
+      p.mode = conv ? half + 1 : 0;
+      if (it & 1) fista_blk_kernel<<<grid, kThreadsB, kSmemBytesB, st>>>(tm_b, tm_a, p);
+      else fista_blk_kernel<<<grid, kThreadsB, kSmemBytesB, st>>>(tm_a, tm_b, p);
+      LASSO_CHECK_LAUNCH();
+      count_launch();
+      if (conv && half == 0) {
+        conv_resid_kernel<<<(unsigned)conv->n_img, 512, conv_smem, st>>>(S.r_buf, a.x, S.row_scale, conv->cin, conv->h,
+                                                                         conv->w, conv->kh, conv->kw, p.ctl);
+        LASSO_CHECK_LAUNCH();
+        count_launch();
+      }
+    }
   }
   // both buffers go back to the caller's units (the stop test may select either one)
   float limit = 32768.0f;

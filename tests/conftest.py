@@ -42,6 +42,9 @@ SOLVER_CASES = [
 ]
 
 
+CONV_CASES = ["conv_8x8_fista", "conv_8x8_plain", "conv_8x8_warmstart", "conv_3x3_auto_earlystop"]
+
+
 @pytest.fixture(scope="session")
 def build_extension():
     """Make sure the in-tree .so exists (nvcc cross-compiles without a GPU)."""

@@ -126,6 +126,39 @@ def main():
     w_deg = ref_dl.update_dict(w.clone(), x, z_deg)
     save("mstep_degenerate", x=x, weight=w, z=z_deg, weight_update=w_deg, zero_atoms=[3, 17])
 
+    # ---- convolutional ISTA (lasso/conv2d/ista.py) -------------------------------------
+    from lasso.conv2d.ista import ista_conv2d as ref_conv
+    g = torch.Generator().manual_seed(77)
+
+    def conv_problem(n, cin, size, filters, ksize, density=0.03):
+        w = torch.randn(filters, cin, ksize, ksize, generator=g)
+        w = w / w.flatten(1).norm(dim=1).view(-1, 1, 1, 1)
+        o = size - ksize + 1
+        code = torch.randn(n, filters, o, o, generator=g) * (torch.rand(n, filters, o, o, generator=g) < density)
+        x = torch.nn.functional.conv_transpose2d(code, w) + 0.01 * torch.randn(n, cin, size, size, generator=g)
+        return x, w, o
+
+    def conv_lr(w):   # a safe step for any kernel size: 1 / (sum over filters of squared l1 norms) bound
+        return 1.0 / float(w.flatten(1).abs().sum(1).square().sum())
+
+    x, w, o = conv_problem(5, 1, 20, 16, 8)
+    lr = conv_lr(w) * 4
+    z0 = torch.zeros(5, 16, o, o)
+    z = ref_conv(x, z0, w, alpha=0.05, fast=True, maxiter=25, lr=lr, tol=0.0)
+    save("conv_8x8_fista", x=x, weight=w, z0=z0, z=z, alpha=0.05, lr=lr, fast=1, maxiter=25, tol=0.0)
+    z = ref_conv(x, z0, w, alpha=0.05, fast=False, maxiter=12, lr=lr, tol=0.0)
+    save("conv_8x8_plain", x=x, weight=w, z0=z0, z=z, alpha=0.05, lr=lr, fast=0, maxiter=12, tol=0.0)
+    z0w = (torch.rand(5, 16, o, o, generator=g) - 0.5) * 0.1
+    z = ref_conv(x, z0w, w, alpha=0.05, fast=True, maxiter=9, lr=lr, tol=0.0)
+    save("conv_8x8_warmstart", x=x, weight=w, z0=z0w, z=z, alpha=0.05, lr=lr, fast=1, maxiter=9, tol=0.0)
+    # odd kernel, several input channels, lr='auto' (Fourier bound, lip_const.py:96-135), early stop
+    x, w, o = conv_problem(4, 4, 12, 12, 3, density=0.05)
+    z0 = torch.zeros(4, 12, o, o)
+    z = ref_conv(x, z0, w, alpha=0.1, fast=True, maxiter=300, lr='auto', tol=1e-3)
+    from lasso.conv2d.lip_const import lip_bound_conv2d as ref_bound
+    save("conv_3x3_auto_earlystop", x=x, weight=w, z0=z0, z=z, alpha=0.1, lr=-1.0, fast=1, maxiter=300,
+         tol=1e-3, lip_bound=float(ref_bound(w, 0)))
+
     for constrained in (True, False):
         x, _ = make_problem(128, 10, 50, seed=21, kind="randn")
         torch.manual_seed(0)

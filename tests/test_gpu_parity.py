@@ -7,7 +7,7 @@ import torch
 
 import lasso_b200
 import oracle
-from conftest import SOLVER_CASES, load_golden
+from conftest import CONV_CASES, SOLVER_CASES, load_golden
 from lasso_b200 import _cabi
 from lasso_b200.linear import (dict_evaluate, dict_learning, lasso_loss, sparse_encode,
                                update_dict, update_dict_ridge)
@@ -443,3 +443,39 @@ def test_verbose_prints_the_reference_losses(dev, capsys):
                          tol=0.0)
     assert len(printed) >= 1
     assert printed == pytest.approx(want, abs=6e-5)
+
+
+@pytest.mark.parametrize("name", CONV_CASES)
+def test_conv2d_ista_matches_reference(dev, name):
+    """lasso.conv2d.ista_conv2d on the k-blocked tcgen05 kernel (im2col -> linear, residual in image
+    space) against the reference's outputs."""
+    from lasso_b200.conv2d import ista_conv2d
+    g = load_golden(name)
+    lr = "auto" if g["lr"] < 0 else g["lr"]
+    z = ista_conv2d(g["x"].to(dev), g["z0"].to(dev), g["weight"].to(dev), alpha=g["alpha"],
+                    fast=bool(g["fast"]), maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
+    assert z.shape == g["z"].shape and z.is_cuda
+    assert rel_fro(z, g["z"]) <= TOL
+    assert support_mismatch(z.cpu(), g["z"]) <= 2e-3
+    # CPU tensors take the same path (H2D, solve, D2H)
+    if name == "conv_8x8_plain":
+        zc = ista_conv2d(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=False,
+                         maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
+        assert not zc.is_cuda and torch.equal(zc, z.cpu())
+
+
+def test_conv2d_config5_shape_against_oracle(dev):
+    # BASELINE config 5: 28x28 images, 512 filters of 8x8 (batch cut to 24 images for the oracle)
+    from lasso_b200.conv2d import ista_conv2d
+    g = torch.Generator().manual_seed(5)
+    n, filters, size, ks = 24, 512, 28, 8
+    w = torch.randn(filters, 1, ks, ks, generator=g)
+    w = w / w.flatten(1).norm(dim=1).view(-1, 1, 1, 1)
+    o = size - ks + 1
+    code = torch.randn(n, filters, o, o, generator=g) * (torch.rand(n, filters, o, o, generator=g) < 0.002)
+    x = torch.nn.functional.conv_transpose2d(code, w) + 0.01 * torch.randn(n, 1, size, size, generator=g)
+    lr, alpha, iters = 2e-3, 0.05, 20
+    z0 = torch.zeros(n, filters, o, o)
+    want = oracle.conv2d_ista(x, z0, w, alpha=alpha, fast=True, maxiter=iters, lr=lr, tol=0.0)
+    got = ista_conv2d(x.to(dev), z0.to(dev), w.to(dev), alpha=alpha, fast=True, maxiter=iters, lr=lr, tol=0.0)
+    assert rel_fro(got, want) <= TOL

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import oracle
-from conftest import SOLVER_CASES, load_golden
+from conftest import CONV_CASES, SOLVER_CASES, load_golden
 from lasso_b200.testing import rel_fro
 
 # Same torch build + same machine gives bit-identical results; a different CPU can
@@ -104,3 +104,30 @@ def test_dict_learning_init_draw_is_the_references():
     torch.manual_seed(0)
     w, _ = oracle.dict_learning(g["x"], 50, alpha=g["alpha"], steps=0)
     assert torch.equal(w, g["weight0"])
+
+
+@pytest.mark.parametrize("name", CONV_CASES)
+def test_conv2d_ista_matches_reference(name):
+    """lasso/conv2d/ista.py:7-49 -- the oracle's restatement against the reference's own outputs."""
+    import lasso_b200
+    from lasso_b200.conv2d import lip_bound_conv2d
+    g = load_golden(name)
+    lr = g["lr"]
+    if lr < 0:      # the case was generated with lr='auto': the Fourier bound must match the reference's
+        bound = float(lip_bound_conv2d(g["weight"], 0))
+        assert abs(bound - g["lip_bound"]) <= 1e-6 * g["lip_bound"]
+        lr = 1 / bound
+    z = oracle.conv2d_ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=bool(g["fast"]),
+                           maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
+    assert rel_fro(z, g["z"]) <= TOL
+
+
+def test_conv2d_lip_bound_error_behaviour():
+    import lasso_b200
+    from lasso_b200.conv2d import ista_conv2d, lip_bound_conv2d
+    with pytest.raises(ValueError):                      # lip_const.py:101-102: odd kernels only
+        lip_bound_conv2d(torch.randn(4, 1, 8, 8), 0)
+    with pytest.raises(ValueError):
+        lip_bound_conv2d(torch.randn(4, 1, 3, 5), 0)
+    with pytest.raises(NotImplementedError):             # ista.py:10-12
+        ista_conv2d(torch.randn(1, 1, 9, 9), torch.zeros(1, 4, 4, 4), torch.randn(4, 1, 3, 3), stride=2)
