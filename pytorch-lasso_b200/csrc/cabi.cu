@@ -268,6 +268,7 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   a.fast = fast ? 1 : 0;
   a.tol_abs = tol_abs;
   a.hist = hist;
+  a.zero_start = z0 == nullptr ? 1 : 0;
   if (path == LASSO_B200_PATH_BLOCKED) {
     // like the resident path: an iterate beyond the fp16 operand range hands the batch to the FFMA
     // kernel, which needs the start codes again (they may alias z_out)
@@ -378,6 +379,7 @@ int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, con
   a.fast = fast ? 1 : 0;
   a.tol_abs = tol_abs;
   a.hist = hist;
+  a.zero_start = z0 == nullptr ? 1 : 0;
   ConvShape shape{n_img, cin, h, w, kh, kw};
   int fell_back = 0;
   if ((rc = fista_blk_run(a, &fell_back, st, &shape))) return rc;

@@ -96,6 +96,7 @@ struct FistaArgs {
   int maxiter, fast;
   double tol_abs;
   double* hist;  // [maxiter] device, zero-initialised
+  int zero_start = 0;  // z_a holds the all-zero start (kernels that rescale the codes may skip it)
 };
 
 // scale factors of the resident kernel (fista_res.cu): all powers of two

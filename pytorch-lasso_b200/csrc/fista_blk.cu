@@ -730,9 +730,10 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
       S.conv_attr_set = true;
     }
     conv_scale_kernel<<<(unsigned)conv->n_img, 256, 0, st>>>(a.x, conv->cin * conv->h * conv->w, conv_P, a.k, S.scal,
-                                                             S.row_scale, a.z_a, 1);
+                                                             S.row_scale, a.z_a, a.zero_start ? 0 : 1);
   } else {
-    blk_rowscale_kernel<<<(unsigned)((a.n + 7) / 8), 256, 0, st>>>(a.x, a.n, a.d, a.k, S.scal, S.row_scale, a.z_a, 1);
+    blk_rowscale_kernel<<<(unsigned)((a.n + 7) / 8), 256, 0, st>>>(a.x, a.n, a.d, a.k, S.scal, S.row_scale, a.z_a,
+                                                                   a.zero_start ? 0 : 1);
   }
   LASSO_CHECK_LAUNCH();
   count_launch(3);
@@ -792,17 +793,21 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
       }
     }
   }
-  // both buffers go back to the caller's units (the stop test may select either one)
+  // back to the caller's units: the buffer that holds z_maxiter, and the other one too when the stop
+  // test may select it
   float limit = 32768.0f;
   if (const char* lim = getenv("LASSO_B200_RES_LIMIT")) limit = (float)atof(lim);   // tests: force the fallback
   const int blocks = (int)std::min<int64_t>((a.n + 7) / 8, (int64_t)S.num_sms * 16);
-  blk_unscale_kernel<<<blocks, 256, 0, st>>>(a.z_a, a.n, a.k, S.row_scale, S.scal, limit, S.flag);
+  float* z_final = (a.maxiter & 1) ? a.z_b : a.z_a;
+  float* z_other = (a.maxiter & 1) ? a.z_a : a.z_b;
+  blk_unscale_kernel<<<blocks, 256, 0, st>>>(z_final, a.n, a.k, S.row_scale, S.scal, limit, S.flag);
   LASSO_CHECK_LAUNCH();
-  if (a.maxiter > 0) {
-    blk_unscale_kernel<<<blocks, 256, 0, st>>>(a.z_b, a.n, a.k, S.row_scale, S.scal, limit, S.flag);
+  count_launch();
+  if (a.maxiter > 0 && a.tol_abs >= 0.0) {
+    blk_unscale_kernel<<<blocks, 256, 0, st>>>(z_other, a.n, a.k, S.row_scale, S.scal, limit, S.flag);
     LASSO_CHECK_LAUNCH();
+    count_launch();
   }
-  count_launch(2);
   int flag = 0;
   cudaError_t e = cudaMemcpyAsync(&flag, S.flag, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
