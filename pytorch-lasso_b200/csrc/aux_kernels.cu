@@ -37,78 +37,150 @@ __global__ void small_gram_kernel(const float* __restrict__ w, int d, int k, int
   if (a < m && b < m) gram[(int64_t)a * m + b] = acc;
 }
 
-// one CTA: normalised power iteration on the m x m Gram, Rayleigh quotient out.
-__global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restrict__ gram, int m,
-                                                          int iters, double* __restrict__ vec,
-                                                          double* __restrict__ out) {
+// m > 64.  The leading eigenvector is found in float32 -- this GPU issues only a few float64
+// operations per clock, and the Rayleigh quotient is second order in the vector error, so a
+// float32-converged vector (error ~1e-6) gives the eigenvalue to ~1e-11 -- and not on G but on
+// G^16 (four trace-normalised squarings, gram_square_kernel): same eigenvectors, the eigenvalue
+// ratio that sets the convergence rate raised to the 16th power, so ~40 iterations do what ~600
+// did (each one streams the m x m matrix through a single SM).  ONE float64 matrix-vector product
+// with the original Gram and a Rayleigh quotient finish.  10.1 ms -> 0.4 ms at m = 289.
+constexpr int kSqTile = 16;
+// C = (A / tr_in) (A / tr_in) for a symmetric m x m matrix; tr_out += trace(C).  A_dbl != nullptr:
+// first squaring, the input is the float64 Gram itself.
+__global__ void gram_square_kernel(const float* __restrict__ a_f, const double* __restrict__ a_dbl, int m,
+                                   const float* __restrict__ tr_in, float* __restrict__ c,
+                                   float* __restrict__ tr_out) {
+  __shared__ float ta[kSqTile][kSqTile + 1], tb[kSqTile][kSqTile + 1];
+  const float scale = 1.0f / fmaxf(tr_in[0], 1e-30f);
+  const int row = blockIdx.y * kSqTile + threadIdx.y, col = blockIdx.x * kSqTile + threadIdx.x;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < m; k0 += kSqTile) {
+    const int ka = k0 + threadIdx.x, kb = k0 + threadIdx.y;
+    float va = 0.f, vb = 0.f;
+    if (row < m && ka < m) va = a_dbl ? (float)a_dbl[(int64_t)row * m + ka] : a_f[(int64_t)row * m + ka];
+    if (kb < m && col < m) vb = a_dbl ? (float)a_dbl[(int64_t)kb * m + col] : a_f[(int64_t)kb * m + col];
+    ta[threadIdx.y][threadIdx.x] = va * scale;
+    tb[threadIdx.y][threadIdx.x] = vb * scale;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSqTile; ++kk) acc = fmaf(ta[threadIdx.y][kk], tb[kk][threadIdx.x], acc);
+    __syncthreads();
+  }
+  if (row < m && col < m) {
+    c[(int64_t)row * m + col] = acc;
+    if (row == col) atomicAdd(tr_out, acc);
+  }
+}
+// tr[0] = trace of the float64 Gram (as float), tr[1..4] = 0
+__global__ void gram_trace_kernel(const double* __restrict__ gram, int m, float* __restrict__ tr) {
+  double s = 0.0;
+  for (int a = threadIdx.x; a < m; a += blockDim.x) s += gram[(int64_t)a * m + a];
+  s = warp_sum(s);
   __shared__ double red[32];
-  __shared__ double s_norm;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += red[wi];
+    tr[0] = (float)t;
+    for (int i = 1; i < 8; ++i) tr[i] = 0.f;
+  }
+}
+__global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restrict__ gram, int m,
+                                                          int iters, const float* __restrict__ gram_f,
+                                                          double* __restrict__ out) {
+  extern __shared__ float pi_smem[];   // v [m], u [m]
+  float* v = pi_smem;
+  float* u = pi_smem + m;
+  __shared__ float redf[32], redm[32];
+  __shared__ double redd[32], rede[32];
+  __shared__ float s_nn, s_dv;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  double* v = vec;       // [m]
-  double* u = vec + m;   // [m]
   for (int a = tid; a < m; a += blockDim.x) {
     // deterministic, non-symmetric start vector
     unsigned h = (unsigned)a * 2654435761u;
-    v[a] = 1.0 + 0.25 * (double)((h >> 8) & 0xffff) / 65536.0;
+    v[a] = 1.0f + 0.25f * (float)((h >> 8) & 0xffff) / 65536.0f;
   }
   __syncthreads();
-  double lambda = 0.0, prev = -1.0;
-  int stable = 0;
+  int calm = 0;
   for (int it = 0; it < iters; ++it) {
     for (int a = warp; a < m; a += nwarps) {
-      double s = 0.0;
-      for (int c = lane; c < m; c += 32) s += gram[(int64_t)a * m + c] * v[c];
-      s = warp_sum(s);
+      const float* row = gram_f + (int64_t)a * m;
+      float s0 = 0.f, s1 = 0.f;
+      int c = lane;
+      for (; c + 32 < m; c += 64) {
+        s0 = fmaf(row[c], v[c], s0);
+        s1 = fmaf(row[c + 32], v[c + 32], s1);
+      }
+      if (c < m) s0 = fmaf(row[c], v[c], s0);
+      float s = s0 + s1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) u[a] = s;
     }
     __syncthreads();
-    double part = 0.0, dotp = 0.0;
+    float part = 0.f;
+    for (int a = tid; a < m; a += blockDim.x) part = fmaf(u[a], u[a], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) redf[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int wi = 0; wi < nwarps; ++wi) s += redf[wi];
+      s_nn = s;
+    }
+    __syncthreads();
+    const float nn = s_nn;
+    if (!(nn > 0.f)) break;   // zero matrix (or NaN): the float64 pass below reports it
+    const float inv = rsqrtf(nn);
+    float dmax = 0.f;
     for (int a = tid; a < m; a += blockDim.x) {
-      part += u[a] * u[a];
-      dotp += u[a] * v[a];
+      const float vn = u[a] * inv;
+      dmax = fmaxf(dmax, fabsf(vn - v[a]));
+      v[a] = vn;
     }
-    part = warp_sum(part);
-    dotp = warp_sum(dotp);
-    if (lane == 0) red[warp] = part;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if (lane == 0) redm[warp] = dmax;
     __syncthreads();
     if (tid == 0) {
-      double s = 0.0;
-      for (int wi = 0; wi < nwarps; ++wi) s += red[wi];
-      s_norm = s;
+      float s = 0.f;
+      for (int wi = 0; wi < nwarps; ++wi) s = fmaxf(s, redm[wi]);
+      s_dv = s;
     }
     __syncthreads();
-    const double nn = s_norm;
-    if (lane == 0) red[warp] = dotp;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int wi = 0; wi < nwarps; ++wi) s += red[wi];
-      red[0] = s;
-    }
-    __syncthreads();
-    // v was unit-norm (after the first step), so v^T M v = <u, v> is the Rayleigh quotient
-    const double vv_dot = red[0];
-    const double nrm = sqrt(nn);
-    __syncthreads();
-    if (nrm == 0.0) {
-      lambda = 0.0;
-      break;
-    }
-    for (int a = tid; a < m; a += blockDim.x) v[a] = u[a] / nrm;
-    __syncthreads();
-    if (it > 0) {
-      lambda = vv_dot;
-      // the Rayleigh quotient converges quadratically in the vector error: once it moves by
-      // less than 1e-13 relative for 4 steps in a row it is good to ~1e-12
-      if (fabs(lambda - prev) <= 1e-13 * fabs(lambda)) {
-        if (++stable >= 4) break;
-      } else {
-        stable = 0;
-      }
-      prev = lambda;
+    // components of a unit vector are O(m^-1/2): stop when none moves by more than float32 noise
+    if (s_dv <= 4e-7f) {
+      if (++calm >= 8) break;
+    } else {
+      calm = 0;
     }
   }
-  if (tid == 0) out[0] = lambda;
+  // float64 Rayleigh quotient of the float32-converged vector:  lambda = v^T G v / v^T v
+  double num = 0.0, den = 0.0;
+  for (int a = warp; a < m; a += nwarps) {
+    double s = 0.0;
+    for (int c = lane; c < m; c += 32) s += gram[(int64_t)a * m + c] * (double)v[c];
+    s = warp_sum(s);
+    if (lane == 0) {
+      num += s * (double)v[a];
+      den += (double)v[a] * (double)v[a];
+    }
+  }
+  if (lane == 0) {
+    redd[warp] = num;
+    rede[warp] = den;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double sn = 0.0, sd = 0.0;
+    for (int wi = 0; wi < nwarps; ++wi) {
+      sn += redd[wi];
+      sd += rede[wi];
+    }
+    out[0] = sd > 0.0 ? sn / sd : 0.0;
+  }
 }
 
 // m <= 64 (the usual case: d = 64): the Gram lives in shared memory, one thread per row, two
@@ -459,7 +531,7 @@ __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, doub
 
 int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
                   cudaStream_t st) {
-  // scratch: [m*m] Gram + [2*m] vectors
+  // scratch (doubles): [m*m] Gram | [2*m] spare | [8] result | then floats: 2 x [m*m] powers of the Gram, [8] traces
   const int row_gram = d <= k ? 1 : 0;
   const int m = row_gram ? d : k;
   const int len = row_gram ? k : d;
@@ -468,7 +540,21 @@ int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double
   LASSO_CHECK_LAUNCH();
   count_launch();
   if (m <= 64) power_iter_small_kernel<<<1, 64, 0, st>>>(scratch, m, iters, l_dev);
-  else power_iter_kernel<<<1, 1024, 0, st>>>(scratch, m, iters, scratch + (size_t)m * m, l_dev);
+  else {
+    // float region behind the doubles: two m x m ping-pong matrices + 8 traces
+    float* f0 = reinterpret_cast<float*>(scratch + (size_t)m * m + 2 * (size_t)m + 8);
+    float* f1 = f0 + (size_t)m * m;
+    float* tr = f1 + (size_t)m * m;
+    gram_trace_kernel<<<1, 256, 0, st>>>(scratch, m, tr);
+    dim3 sgrid((m + kSqTile - 1) / kSqTile, (m + kSqTile - 1) / kSqTile), sblock(kSqTile, kSqTile);
+    gram_square_kernel<<<sgrid, sblock, 0, st>>>(nullptr, scratch, m, tr + 0, f0, tr + 1);   // G^2
+    gram_square_kernel<<<sgrid, sblock, 0, st>>>(f0, nullptr, m, tr + 1, f1, tr + 2);        // G^4
+    gram_square_kernel<<<sgrid, sblock, 0, st>>>(f1, nullptr, m, tr + 2, f0, tr + 3);        // G^8
+    gram_square_kernel<<<sgrid, sblock, 0, st>>>(f0, nullptr, m, tr + 3, f1, tr + 4);        // G^16
+    LASSO_CHECK_LAUNCH();
+    count_launch(5);
+    power_iter_kernel<<<1, 1024, 2 * (size_t)m * sizeof(float), st>>>(scratch, m, iters, f1, l_dev);
+  }
   LASSO_CHECK_LAUNCH();
   count_launch();
   return LASSO_B200_OK;
