@@ -2,6 +2,8 @@
 // M-step sufficient statistics (Gram matrices) and the Gram-space atom sweep.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lasso {
@@ -527,6 +529,133 @@ __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, doub
   }
 }
 
+// Cluster variant for dictionaries that do not fit one SM's shared memory (e.g. the reference
+// notebook's d = 289, k = 300).  The rows i of u_i = B[j,i] - sum_{l != j} D[i,l] A[j,l] are
+// independent, so a cluster of kSweepCluster CTAs splits them: each CTA keeps its slice of the
+// dictionary rows in shared memory for the whole sweep and only the squared norm of u crosses CTAs
+// (every CTA stores its partial into every peer's shared memory, then one cluster barrier).  The
+// partials are summed in rank order by every CTA, so all of them see the same |u| bit for bit.
+// Same arithmetic as dict_sweep_smem_kernel (float32 inner products without the diagonal term,
+// float64 u / norm); rows of A, B arrive by 8-byte cp.async, so d and k may be odd.
+constexpr int kSweepCluster = 8;
+constexpr int kSweepClusterThreads = 512;
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__global__ void __cluster_dims__(kSweepCluster, 1, 1) __launch_bounds__(kSweepClusterThreads)
+    dict_sweep_cluster_kernel(float* dict, double* gzz, double* gzx, int d, int k, int dl, double eps,
+                              int* __restrict__ zeroed) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int i_lo = min(d, rank * dl), nloc = min(d, i_lo + dl) - i_lo;    // this CTA's rows of D / u
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  double* arow = reinterpret_cast<double*>(sweep_smem);                   // [depth][k]
+  double* brow = arow + kSweepDepth * k;                                  // [depth][dl]
+  double* us = brow + kSweepDepth * dl;                                   // [dl]
+  double* parts = us + dl;                                                // [2][cluster] squared-norm partials
+  float* ds = reinterpret_cast<float*>(parts + 2 * kSweepCluster);        // [dl][k]
+  float* af = ds + (size_t)dl * k;                                        // [k]
+  unsigned char* dead = reinterpret_cast<unsigned char*>(af + k);         // [k]
+  __shared__ double s_inv, s_nrm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  auto prefetch = [&](int j) {
+    if (j < k) {
+      const int slot = j % kSweepDepth;
+      for (int t = tid; t < k + nloc; t += blockDim.x) {
+        if (t < k) cp_async8(arow + slot * k + t, gzz + (int64_t)j * k + t);
+        else cp_async8(brow + slot * dl + (t - k), gzx + (int64_t)j * d + i_lo + (t - k));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int e = tid; e < nloc * k; e += blockDim.x) ds[e] = dict[(int64_t)i_lo * k + e];
+  for (int l = tid; l < k; l += blockDim.x) dead[l] = 0;
+  for (int j = 0; j < kSweepDepth - 1; ++j) prefetch(j);
+  for (int j = 0; j < k; ++j) {
+    prefetch(j + kSweepDepth - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kSweepDepth - 1) : "memory");
+    __syncthreads();
+    const double* aj = arow + (j % kSweepDepth) * k;
+    const double* bj = brow + (j % kSweepDepth) * dl;
+    for (int l = tid; l < k; l += blockDim.x) af[l] = (l == j || dead[l]) ? 0.f : (float)aj[l];
+    __syncthreads();
+    for (int i0 = warp; i0 < nloc; i0 += 2 * nwarps) {                    // two rows per warp in flight
+      const int i1 = i0 + nwarps;
+      const bool two = i1 < nloc;
+      const float* r0 = ds + (size_t)i0 * k;
+      const float* r1 = ds + (size_t)(two ? i1 : i0) * k;
+      float s0 = 0.f, s1 = 0.f;
+      for (int l = lane; l < k; l += 32) {
+        const float a = af[l];
+        s0 = fmaf(r0[l], a, s0);
+        s1 = fmaf(r1[l], a, s1);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if (lane == 0) {
+        us[i0] = bj[i0] - (double)s0;
+        if (two) us[i1] = bj[i1] - (double)s1;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {                                                      // this CTA's share of |u|^2 to every peer
+      double part = 0.0;
+      for (int i = lane; i < nloc; i += 32) part += us[i] * us[i];
+      part = warp_sum(part);
+      if (lane < kSweepCluster) cluster.map_shared_rank(parts, lane)[(j & 1) * kSweepCluster + rank] = part;
+    }
+    cluster.sync();
+    if (warp == 0) {
+      double ss = 0.0;
+#pragma unroll
+      for (int c = 0; c < kSweepCluster; ++c) ss += parts[(j & 1) * kSweepCluster + c];
+      double inv = 0.0;
+      if (ss > 0.0 && ss < 1e300) {
+        if (ss < 1e-30 || ss > 1e30) {
+          inv = 1.0 / sqrt(ss);
+        } else {
+          inv = (double)rsqrtf((float)ss);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) inv = inv * (1.5 - 0.5 * ss * inv * inv);
+        }
+      }
+      if (lane == 0) {
+        s_inv = inv;
+        s_nrm = ss * inv;
+      }
+    }
+    __syncthreads();
+    const double inv = s_inv, nrm = s_nrm;
+    if (nrm < eps) {
+      // degenerate atom (dict_learning.py:92-98): statistics row/column dropped, atom left for the
+      // caller to redraw; the copies already prefetched are masked through dead[]
+      if (rank == 0) {
+        for (int l = tid; l < k; l += blockDim.x) {
+          gzz[(int64_t)j * k + l] = 0.0;
+          gzz[(int64_t)l * k + j] = 0.0;
+        }
+        for (int i = tid; i < d; i += blockDim.x) gzx[(int64_t)j * d + i] = 0.0;
+        if (tid == 0) zeroed[j] = 1;
+      }
+      if (tid == 0) dead[j] = 1;
+    } else {
+      if (rank == 0 && tid == 0) zeroed[j] = 0;
+      for (int i = tid; i < nloc; i += blockDim.x) {
+        const float v = (float)(us[i] * inv);
+        ds[(size_t)i * k + j] = v;
+        dict[(int64_t)(i_lo + i) * k + j] = v;
+      }
+    }
+  }
+  cluster.sync();   // no CTA leaves while a peer may still store into its shared memory
+}
+
 }  // namespace
 
 int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
@@ -588,6 +717,23 @@ int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double 
     if (const char* t = getenv("LASSO_B200_SWEEP_THREADS")) threads = atoi(t);
     if (threads < 256 || threads > 1024 || (threads % 32) != 0 || k / 2 + d / 2 > threads) threads = 1024;
     dict_sweep_smem_kernel<<<1, threads, smem, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+    return LASSO_B200_OK;
+  }
+  // larger dictionaries: rows split over a cluster of CTAs
+  const int dl = (d + kSweepCluster - 1) / kSweepCluster;
+  const size_t csmem = sizeof(double) * ((size_t)kSweepDepth * (k + dl) + dl + 2 * kSweepCluster) +
+                       sizeof(float) * ((size_t)dl * k + k) + (size_t)k;
+  if (redraw == nullptr && csmem <= 200 * 1024 && getenv("LASSO_B200_SWEEP_NO_CLUSTER") == nullptr) {
+    static bool cattr_set = false;
+    if (!cattr_set) {
+      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_cluster_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      cattr_set = true;
+    }
+    dict_sweep_cluster_kernel<<<kSweepCluster, kSweepClusterThreads, csmem, st>>>(dict, gzz, gzx, d, k, dl, eps,
+                                                                                  zeroed);
     LASSO_CHECK_LAUNCH();
     count_launch();
     return LASSO_B200_OK;

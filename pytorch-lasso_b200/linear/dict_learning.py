@@ -70,15 +70,19 @@ def update_dict(dictionary, X, Z, random_seed=None, positive=False, eps=1e-10, g
     gzz, gzx = _statistics(X, Z, group)
     zeroed = _cabi.dict_update_gram(dictionary, gzz, gzx, eps=eps, redraw=None)
     if bool(zeroed.any()):  # one sync per sweep (the reference syncs once per atom)
+        # degenerate atoms (dict_learning.py:91-98): fresh N(0,1) atoms, unit norm, their codes dropped.
+        # All of them are drawn in ONE call (the reference draws them one by one inside its atom loop;
+        # early EM steps of a large dictionary can have dozens, and a handful of tiny launches per
+        # atom dominated the M-step).
+        idx = zeroed.nonzero().flatten()
         d = dictionary.size(0)
-        for j in zeroed.nonzero().flatten().tolist():
-            atom = torch.empty(d, device=dictionary.device).normal_()
-            if _world(group) > 1:
-                torch.distributed.broadcast(atom, src=torch.distributed.get_global_rank(group, 0)
-                                            if group is not torch.distributed.group.WORLD else 0,
-                                            group=group)
-            dictionary[:, j] = atom / atom.norm()
-            Z[:, j].zero_()
+        atoms = torch.empty(idx.numel(), d, device=dictionary.device).normal_()
+        if _world(group) > 1:
+            torch.distributed.broadcast(atoms, src=torch.distributed.get_global_rank(group, 0)
+                                        if group is not torch.distributed.group.WORLD else 0,
+                                        group=group)
+        dictionary[:, idx] = (atoms / atoms.norm(dim=1, keepdim=True)).T
+        Z[:, idx] = 0
     return dictionary
 
 

@@ -372,6 +372,33 @@ def test_update_dict_matches_reference(dev):
     assert v.shape == g["weight_ridge"].shape and rel_fro(v, g["weight_ridge"]) <= TOL
 
 
+@pytest.mark.parametrize("n,d,k", [(3000, 150, 300), (1500, 289, 300), (2000, 9, 600), (1500, 31, 77)])
+def test_update_dict_large_dictionary(dev, n, d, k):
+    # dictionaries beyond the single-SM sweep kernel (d * k floats do not fit its shared memory, k > 256,
+    # or odd d / k): the atom sweep runs on a cluster of CTAs, each holding a slice of the rows
+    x, w = make_problem(n, d, k, seed=12)
+    z = sparse_encode(x.to(dev), w.to(dev), alpha=0.1, maxiter=25, tol=0.0)
+    want = oracle.update_dict(w.clone(), x, z.cpu().clone())
+    got = update_dict(w.to(dev).clone(), x.to(dev), z.clone())
+    assert rel_fro(got, want) <= TOL
+
+
+def test_update_dict_large_dictionary_degenerate(dev):
+    # unused atoms in the cluster sweep: flagged, re-drawn with unit norm, their codes dropped; the others
+    # match the oracle (which drops the same atoms)
+    n, d, k = 1500, 150, 300
+    x, w = make_problem(n, d, k, seed=13)
+    z = sparse_encode(x.to(dev), w.to(dev), alpha=0.1, maxiter=25, tol=0.0)
+    unused = [3, 150, 299]
+    z[:, unused] = 0
+    want = oracle.update_dict(w.clone(), x, z.cpu().clone())
+    got = update_dict(w.to(dev).clone(), x.to(dev), z, random_seed=5)
+    keep = [j for j in range(k) if j not in unused]
+    assert rel_fro(got[:, keep], want[:, keep]) <= TOL
+    for j in unused:
+        assert abs(float(got[:, j].norm()) - 1.0) <= 1e-6
+
+
 def test_update_dict_degenerate_atoms(dev):
     g = load_golden("mstep_degenerate")
     zero_atoms = [int(a) for a in g["zero_atoms"]]
