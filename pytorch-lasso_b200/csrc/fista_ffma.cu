@@ -73,8 +73,10 @@ struct StepParams {
 // MODE 3 = line-search trial: cand = softshrink(z_cur - lr * aux, lam) -> out,  (ista.py:40)
 //          out2 += { sum (cand W^T - x)^2, sum |cand|, sum dz * aux, sum dz^2 } (ista.py:26-35)
 template <int TM, int MODE>
-__global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
+__global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(StepParams p) {
   constexpr int RPT = TM / 16;  // rows per thread
+  constexpr int A_IT = (TM * (kCk / 4) + kThreads - 1) / kThreads;   // float4 per thread of a Y chunk
+  constexpr int W_IT = kBlk * (kCk / 4) / kThreads;                  // float4 per thread of a W chunk
   extern __shared__ __align__(16) float smem[];
   const int d_pad = (p.d + 3) & ~3;
   const int r_ld = d_pad + kPad;
@@ -99,28 +101,44 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
     const int64_t row0 = tile * TM;
 
     // ---------------- phase 1: R = Y W^T - X ------------------------------
-    for (int db = 0; db < p.d; db += kBlk) {
-      float acc[RPT][4];
+    // The Y and W chunks of step j0 + kCk are fetched into registers (fetch1) before the products of
+    // step j0 are formed, and written to shared memory (commit1) after them, so the global / L2 latency
+    // of the staging hides behind the FFMA block of the same CTA.
+    float4 ra[A_IT], rp[A_IT], rg[A_IT], rw[W_IT];
+    auto fetch1 = [&](int db, int j0) {
 #pragma unroll
-      for (int r = 0; r < RPT; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-
-      for (int j0 = 0; j0 < p.k; j0 += kCk) {
-        __syncthreads();
-        // stage Y chunk [TM][kCk] and W chunk [kBlk][kCk]  (both contraction-contiguous)
-        for (int e = tid; e < TM * (kCk / 4); e += kThreads) {
+      for (int it = 0; it < A_IT; ++it) {
+        const int e = tid + it * kThreads;
+        if (e < TM * (kCk / 4)) {
           const int r = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
-          float4 zc = ld4(p.z_cur, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+          ra[it] = ld4(p.z_cur, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+          if (MODE == 0 && p.use_prev) rp[it] = ld4(p.z_io, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+          if (MODE == 3) rg[it] = ld4(p.aux, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < W_IT; ++it) {
+        const int e = tid + it * kThreads;
+        const int i = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
+        rw[it] = ld4(p.w, db + i, j0 + c4, p.d, p.k, p.k, kvec);
+      }
+    };
+    auto commit1 = [&](int db, int j0) {
+#pragma unroll
+      for (int it = 0; it < A_IT; ++it) {
+        const int e = tid + it * kThreads;
+        if (e < TM * (kCk / 4)) {
+          const int r = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
+          float4 zc = ra[it];
           if (MODE == 0 && p.use_prev) {
-            float4 zp = ld4(p.z_io, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+            const float4 zp = rp[it];
             zc.x = momentum_point(zc.x, zp.x, p.beta);
             zc.y = momentum_point(zc.y, zp.y, p.beta);
             zc.z = momentum_point(zc.z, zp.z, p.beta);
             zc.w = momentum_point(zc.w, zp.w, p.beta);
           }
           if (MODE == 3) {
-            const float4 g = ld4(p.aux, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
+            const float4 g = rg[it];
             float4 cd;
             cd.x = ista_update(zc.x, g.x, p.lr, p.lam);
             cd.y = ista_update(zc.y, g.y, p.lr, p.lam);
@@ -139,12 +157,27 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
             acc_b += (double)(fabsf(zc.x) + fabsf(zc.y)) + (double)(fabsf(zc.z) + fabsf(zc.w));
           *reinterpret_cast<float4*>(&As[r * (kCk + kPad) + c4]) = zc;
         }
-        for (int e = tid; e < kBlk * (kCk / 4); e += kThreads) {
-          const int i = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
-          float4 wv = ld4(p.w, db + i, j0 + c4, p.d, p.k, p.k, kvec);
-          *reinterpret_cast<float4*>(&Ws[i * (kCk + kPad) + c4]) = wv;
-        }
+      }
+#pragma unroll
+      for (int it = 0; it < W_IT; ++it) {
+        const int e = tid + it * kThreads;
+        const int i = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
+        *reinterpret_cast<float4*>(&Ws[i * (kCk + kPad) + c4]) = rw[it];
+      }
+    };
+    for (int db = 0; db < p.d; db += kBlk) {
+      float acc[RPT][4];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+      fetch1(db, 0);
+      for (int j0 = 0; j0 < p.k; j0 += kCk) {
         __syncthreads();
+        commit1(db, j0);
+        __syncthreads();
+        if (j0 + kCk < p.k) fetch1(db, j0 + kCk);
 #pragma unroll
         for (int jj = 0; jj < kCk; jj += 4) {
           float4 a[RPT], b[4];
@@ -181,6 +214,22 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
     if (MODE == 1 || MODE == 3) continue;
 
     // ---------------- phase 2: G = R W, fused update ----------------------
+    auto fetch2 = [&](int j0, int i0) {   // W chunk [kCk][kBlk] (output-contiguous), one step ahead
+#pragma unroll
+      for (int it = 0; it < W_IT; ++it) {
+        const int e = tid + it * kThreads;
+        const int ii = e / (kBlk / 4), c4 = (e % (kBlk / 4)) * 4;
+        rw[it] = ld4(p.w, i0 + ii, j0 + c4, p.d, p.k, p.k, kvec);
+      }
+    };
+    auto commit2 = [&]() {
+#pragma unroll
+      for (int it = 0; it < W_IT; ++it) {
+        const int e = tid + it * kThreads;
+        const int ii = e / (kBlk / 4), c4 = (e % (kBlk / 4)) * 4;
+        *reinterpret_cast<float4*>(&Ws[ii * (kBlk + kPad) + c4]) = rw[it];
+      }
+    };
     for (int j0 = 0; j0 < p.k; j0 += kBlk) {
       float acc[RPT][4];
 #pragma unroll
@@ -188,15 +237,12 @@ __global__ void __launch_bounds__(kThreads) fista_ffma_kernel(StepParams p) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 
+      fetch2(j0, 0);
       for (int i0 = 0; i0 < d_pad; i0 += kCk) {
         __syncthreads();
-        // stage W chunk [kCk][kBlk] (output-contiguous)
-        for (int e = tid; e < kCk * (kBlk / 4); e += kThreads) {
-          const int ii = e / (kBlk / 4), c4 = (e % (kBlk / 4)) * 4;
-          float4 wv = ld4(p.w, i0 + ii, j0 + c4, p.d, p.k, p.k, kvec);
-          *reinterpret_cast<float4*>(&Ws[ii * (kBlk + kPad) + c4]) = wv;
-        }
+        commit2();
         __syncthreads();
+        if (i0 + kCk < d_pad) fetch2(j0, i0 + kCk);
         const int imax = min(kCk, d_pad - i0);
         for (int ii = 0; ii < imax; ii += 4) {
           float4 a[RPT], b[4];
@@ -330,9 +376,9 @@ int pick_tm(int d) {
     const int tm = atoi(e);
     if ((tm == 64 || tm == 32 || tm == 16) && smem_bytes(tm, d) <= budget) return tm;
   }
-  // 64-row tiles while four CTAs (32 warps) still fit one SM; beyond that (d > 148) 32-row tiles keep the
-  // occupancy and measured 5-9 % faster (tools/ffma_tm.py: d = 200, 289)
-  if (smem_bytes(64, d) <= 56 * 1024) return 64;
+  // 64-row tiles while two CTAs fit one SM (tools/ffma_tm.py: with the register-staged prefetch they beat
+  // 32-row tiles by 4-20 % at d = 200 and 289)
+  if (smem_bytes(64, d) <= 96 * 1024) return 64;
   if (smem_bytes(32, d) <= budget) return 32;
   if (smem_bytes(16, d) <= budget) return 16;
   return 0;

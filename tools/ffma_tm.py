@@ -6,10 +6,13 @@ import torch, lasso_b200
 from lasso_b200.linear import sparse_encode
 from lasso_b200.testing import make_problem
 dev = torch.device("cuda", 0)
-for n, d, k in ((10000, 289, 300), (65536, 289, 300), (10000, 200, 512)):
+shapes = ((10000, 289, 300), (65536, 289, 300), (10000, 200, 512))
+if os.environ.get("FFMA_ONE"):   # one shape, default tile (for an ncu capture)
+    shapes = ((65536, 289, 300),)
+for n, d, k in shapes:
     x, w = make_problem(n, d, k, seed=0)
     x, w = x.to(dev), w.to(dev)
-    for tm in ("64", "32", "16"):
+    for tm in (("64", "32", "16") if not os.environ.get("FFMA_ONE") else ("64",)):
         os.environ["LASSO_B200_FFMA_TM"] = tm
         f = lambda: sparse_encode(x, w, 0.5, maxiter=20, lr=0.01)
         f(); torch.cuda.synchronize(); t0 = time.perf_counter()
