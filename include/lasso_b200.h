@@ -170,11 +170,13 @@ int32_t lasso_b200_gram_f32(const float* z, const float* x, int64_t n, int32_t d
  *             left for the caller to re-draw (its statistics are zeroed either way)
  *   zeroed    device [k] int32: 1 for degenerate atoms -- the caller must zero
  *             the code column z[:,j] (dict_learning.py:98)
+ *   positive  non-zero: every atom (and every re-drawn atom) is clamped at zero
+ *             before it is normalised (update_dict(positive=True), dict_learning.py:87-88, 94-95)
  */
 int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gram_zx,
                                         int32_t d, int32_t k, double eps,
                                         const float* redraw, int32_t* zeroed,
-                                        void* stream);
+                                        int32_t positive, void* stream);
 
 /*
  * Building blocks of the slow path of ista(): backtrack=True (Beck-Teboulle line search with

@@ -202,8 +202,8 @@ def lasso_loss(x, z, weight, alpha=1.0):
     return (0.5 * (x - recon).pow(2).sum() + alpha * z.abs().sum()) / x.size(0)
 
 
-def update_dict(dictionary, x, z, eps=1e-10, redraw=None):
-    """Sequential atom update of dict_learning.py:56-103 (positive=False).
+def update_dict(dictionary, x, z, eps=1e-10, redraw=None, positive=False):
+    """Sequential atom update of dict_learning.py:56-103 (``positive``: the clamp of :87-88, :94-95).
 
     In place on ``dictionary`` and ``z`` like the reference.  ``redraw`` is an
     optional callable ``(d,) -> tensor`` that supplies the replacement for a
@@ -213,12 +213,16 @@ def update_dict(dictionary, x, z, eps=1e-10, redraw=None):
     for j in range(dictionary.size(1)):
         resid += torch.outer(z[:, j], dictionary[:, j])
         dictionary[:, j] = torch.matmul(z[:, j], resid)
+        if positive:
+            dictionary[:, j].clamp_(0, None)
         nrm = dictionary[:, j].norm()
         if nrm < eps:
             if redraw is None:
                 dictionary[:, j].normal_()
             else:
                 dictionary[:, j] = redraw(dictionary.size(0))
+            if positive:
+                dictionary[:, j].clamp_(0, None)
             dictionary[:, j] /= dictionary[:, j].norm()
             z[:, j].zero_()
         else:
@@ -227,7 +231,7 @@ def update_dict(dictionary, x, z, eps=1e-10, redraw=None):
     return dictionary
 
 
-def update_dict_gram(dictionary, gram_zz, gram_zx, eps=1e-10, redraw=None):
+def update_dict_gram(dictionary, gram_zz, gram_zx, eps=1e-10, redraw=None, positive=False):
     """Gram-space restatement of the same Gauss-Seidel sweep.
 
     With A = Z^T Z (k x k) and B = Z^T X (k x d) the un-normalised atom is
@@ -241,10 +245,14 @@ def update_dict_gram(dictionary, gram_zz, gram_zx, eps=1e-10, redraw=None):
     zeroed = []
     for j in range(dmat.size(1)):
         u = b[j] - dmat @ a[:, j] + a[j, j] * dmat[:, j]
+        if positive:
+            u = u.clamp(min=0)
         nrm = u.norm()
         if nrm < eps:
             u = torch.randn(dmat.size(0), dtype=torch.float64) if redraw is None \
                 else redraw(dmat.size(0)).to(torch.float64)
+            if positive:
+                u = u.clamp(min=0)
             dmat[:, j] = u / u.norm()
             a[j, :] = 0
             a[:, j] = 0

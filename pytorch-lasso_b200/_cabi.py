@@ -76,7 +76,7 @@ def _declare(lib):
     lib.lasso_b200_gram_f32.restype = i32
     lib.lasso_b200_gram_f32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     lib.lasso_b200_dict_update_gram_f32.restype = i32
-    lib.lasso_b200_dict_update_gram_f32.argtypes = [vp, vp, vp, i32, i32, f64, vp, vp, vp]
+    lib.lasso_b200_dict_update_gram_f32.argtypes = [vp, vp, vp, i32, i32, f64, vp, vp, i32, vp]
     lib.lasso_b200_gradient_f32.restype = i32
     lib.lasso_b200_gradient_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.lasso_b200_linesearch_trial_f32.restype = i32
@@ -249,7 +249,7 @@ def gram(z, x, out_zz=None, out_zx=None):
     return gzz, gzx
 
 
-def dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None):
+def dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None, positive=False):
     """In-place Gram-space atom sweep; returns int32 device mask of re-drawn atoms."""
     lib = load()
     if not (dictionary.is_cuda and dictionary.dtype == torch.float32 and dictionary.is_contiguous()):
@@ -262,7 +262,7 @@ def dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None):
         _check(lib.lasso_b200_dict_update_gram_f32(
             dictionary.data_ptr(), gzz.data_ptr(), gzx.data_ptr(), d, k, float(eps),
             redraw.data_ptr() if redraw is not None else None, zeroed.data_ptr(),
-            _stream_ptr(dictionary.device)))
+            1 if positive else 0, _stream_ptr(dictionary.device)))
     return zeroed
 
 

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(1024) dict_sweep_kernel(float* dict, double* g
                                                           int d, int k, double eps,
                                                           const float* __restrict__ redraw,
                                                           int* __restrict__ zeroed,
-                                                          double* __restrict__ u) {
+                                                          double* __restrict__ u, int positive) {
   __shared__ double red[32];
   __shared__ double s_val;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -339,7 +339,10 @@ __global__ void __launch_bounds__(1024) dict_sweep_kernel(float* dict, double* g
       for (int l = lane; l < k; l += 32)
         s += (double)dict[(int64_t)i * k + l] * gzz[(int64_t)j * k + l];
       s = warp_sum(s);
-      if (lane == 0) u[i] = gzx[(int64_t)j * d + i] - s + ajj * (double)dict[(int64_t)i * k + j];
+      if (lane == 0) {
+        const double v = gzx[(int64_t)j * d + i] - s + ajj * (double)dict[(int64_t)i * k + j];
+        u[i] = positive ? fmax(v, 0.0) : v;     // positive: clamp before the norm (dict_learning.py:87-88)
+      }
     }
     __syncthreads();
     double part = 0.0;
@@ -369,7 +372,8 @@ __global__ void __launch_bounds__(1024) dict_sweep_kernel(float* dict, double* g
         __syncthreads();
         part = 0.0;
         for (int i = tid; i < d; i += blockDim.x) {
-          const double r = (double)redraw[(int64_t)i * k + j];
+          double r = (double)redraw[(int64_t)i * k + j];
+          if (positive) r = fmax(r, 0.0);           // dict_learning.py:94-95
           u[i] = r;
           part += r * r;
         }
@@ -416,7 +420,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, double* gzz, double* gzx, int d,
                                                                int k, double eps,
                                                                const float* __restrict__ redraw,
-                                                               int* __restrict__ zeroed) {
+                                                               int* __restrict__ zeroed, int positive) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   double* arow = reinterpret_cast<double*>(sweep_smem);                               // [depth][k]
   double* brow = arow + kSweepDepth * k;                                              // [depth][d]
@@ -467,8 +471,9 @@ __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, doub
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       }
       if (lane == 0) {
-        us[i0] = bj[i0] - (double)s0;
-        if (two) us[i1] = bj[i1] - (double)s1;
+        const double v0 = bj[i0] - (double)s0, v1 = two ? bj[i1] - (double)s1 : 0.0;
+        us[i0] = positive ? fmax(v0, 0.0) : v0;   // positive: clamp before the norm (dict_learning.py:87-88)
+        if (two) us[i1] = positive ? fmax(v1, 0.0) : v1;
       }
     }
     __syncthreads();
@@ -510,7 +515,10 @@ __global__ void __launch_bounds__(1024) dict_sweep_smem_kernel(float* dict, doub
       nrm = 0.0;
       if (redraw != nullptr) {
         __syncthreads();
-        for (int i = tid; i < d; i += blockDim.x) us[i] = (double)redraw[(int64_t)i * k + j];
+        for (int i = tid; i < d; i += blockDim.x) {
+          const double r = (double)redraw[(int64_t)i * k + j];
+          us[i] = positive ? fmax(r, 0.0) : r;      // dict_learning.py:94-95
+        }
         __syncthreads();
         part = 0.0;
         for (int i = lane; i < d; i += 32) part += us[i] * us[i];
@@ -546,7 +554,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 }
 __global__ void __cluster_dims__(kSweepCluster, 1, 1) __launch_bounds__(kSweepClusterThreads)
     dict_sweep_cluster_kernel(float* dict, double* gzz, double* gzx, int d, int k, int dl, double eps,
-                              int* __restrict__ zeroed) {
+                              int* __restrict__ zeroed, int positive) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -599,8 +607,9 @@ __global__ void __cluster_dims__(kSweepCluster, 1, 1) __launch_bounds__(kSweepCl
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       }
       if (lane == 0) {
-        us[i0] = bj[i0] - (double)s0;
-        if (two) us[i1] = bj[i1] - (double)s1;
+        const double v0 = bj[i0] - (double)s0, v1 = two ? bj[i1] - (double)s1 : 0.0;
+        us[i0] = positive ? fmax(v0, 0.0) : v0;   // positive: clamp before the norm (dict_learning.py:87-88)
+        if (two) us[i1] = positive ? fmax(v1, 0.0) : v1;
       }
     }
     __syncthreads();
@@ -703,7 +712,7 @@ int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gz
 }
 
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
-                    const float* redraw, int* zeroed, cudaStream_t st) {
+                    const float* redraw, int* zeroed, int positive, cudaStream_t st) {
   const size_t smem = sizeof(double) * ((size_t)kSweepDepth * (k + d) + d) +
                       sizeof(float) * ((size_t)d * k + k) + (size_t)k;
   if (smem <= 200 * 1024 && k <= 32 * kSweepMaxPerLane && (k % 2) == 0 && (d % 2) == 0 && k / 2 + d / 2 <= 1024) {
@@ -716,7 +725,7 @@ int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double 
     int threads = 1024;
     if (const char* t = getenv("LASSO_B200_SWEEP_THREADS")) threads = atoi(t);
     if (threads < 256 || threads > 1024 || (threads % 32) != 0 || k / 2 + d / 2 > threads) threads = 1024;
-    dict_sweep_smem_kernel<<<1, threads, smem, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed);
+    dict_sweep_smem_kernel<<<1, threads, smem, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed, positive);
     LASSO_CHECK_LAUNCH();
     count_launch();
     return LASSO_B200_OK;
@@ -733,14 +742,14 @@ int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double 
       cattr_set = true;
     }
     dict_sweep_cluster_kernel<<<kSweepCluster, kSweepClusterThreads, csmem, st>>>(dict, gzz, gzx, d, k, dl, eps,
-                                                                                  zeroed);
+                                                                                  zeroed, positive);
     LASSO_CHECK_LAUNCH();
     count_launch();
     return LASSO_B200_OK;
   }
   double* u = nullptr;
   LASSO_CUDA_TRY(cudaMallocAsync(&u, sizeof(double) * (size_t)d, st));
-  dict_sweep_kernel<<<1, 1024, 0, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed, u);
+  dict_sweep_kernel<<<1, 1024, 0, st>>>(dict, gzz, gzx, d, k, eps, redraw, zeroed, u, positive);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(u, st);
   if (e != cudaSuccess) {

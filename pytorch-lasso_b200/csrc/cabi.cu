@@ -652,13 +652,13 @@ int32_t lasso_b200_gram_f32(const float* z, const float* x, int64_t n, int32_t d
 
 int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gram_zx, int32_t d,
                                         int32_t k, double eps, const float* redraw,
-                                        int32_t* zeroed, void* stream) {
+                                        int32_t* zeroed, int32_t positive, void* stream) {
   t_error[0] = 0;
   if (!dict || !gram_zz || !gram_zx || !zeroed || d <= 0 || k <= 0) {
     set_error("invalid argument to dict_update_gram");
     return LASSO_B200_ERR_INVALID;
   }
-  return dict_update_run(dict, gram_zz, gram_zx, d, k, eps, redraw, zeroed, (cudaStream_t)stream);
+  return dict_update_run(dict, gram_zz, gram_zx, d, k, eps, redraw, zeroed, positive ? 1 : 0, (cudaStream_t)stream);
 }
 
 int32_t lasso_b200_gradient_f32(const float* x, const float* point, const float* weight, int64_t n,

@@ -143,6 +143,6 @@ int momentum_run(const float* z_next, const float* z, float beta, float* y, int6
 int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz,
              double* gzx, cudaStream_t st);
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
-                    const float* redraw, int* zeroed, cudaStream_t st);
+                    const float* redraw, int* zeroed, int positive, cudaStream_t st);
 
 }  // namespace lasso

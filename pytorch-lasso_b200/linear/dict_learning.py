@@ -61,14 +61,12 @@ def _statistics(X, Z, group):
 def update_dict(dictionary, X, Z, random_seed=None, positive=False, eps=1e-10, group=None):
     """Block-coordinate atom update, in place on ``dictionary`` (and on ``Z`` for
     degenerate atoms) like the reference (dict_learning.py:56-103)."""
-    if positive:
-        raise NotImplementedError("positive=True is not implemented in lasso_b200")
     if random_seed is not None:
         torch.manual_seed(random_seed)
     if not (dictionary.is_cuda and dictionary.is_contiguous() and dictionary.dtype == torch.float32):
         raise _cabi.LassoB200Error("dictionary must be a contiguous float32 CUDA tensor")
     gzz, gzx = _statistics(X, Z, group)
-    zeroed = _cabi.dict_update_gram(dictionary, gzz, gzx, eps=eps, redraw=None)
+    zeroed = _cabi.dict_update_gram(dictionary, gzz, gzx, eps=eps, redraw=None, positive=positive)
     if bool(zeroed.any()):  # one sync per sweep (the reference syncs once per atom)
         # degenerate atoms (dict_learning.py:91-98): fresh N(0,1) atoms, unit norm, their codes dropped.
         # All of them are drawn in ONE call (the reference draws them one by one inside its atom loop;
@@ -77,6 +75,8 @@ def update_dict(dictionary, X, Z, random_seed=None, positive=False, eps=1e-10, g
         idx = zeroed.nonzero().flatten()
         d = dictionary.size(0)
         atoms = torch.empty(idx.numel(), d, device=dictionary.device).normal_()
+        if positive:
+            atoms.clamp_(0, None)      # dict_learning.py:94-95
         if _world(group) > 1:
             torch.distributed.broadcast(atoms, src=torch.distributed.get_global_rank(group, 0)
                                         if group is not torch.distributed.group.WORLD else 0,

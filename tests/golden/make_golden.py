@@ -126,6 +126,10 @@ def main():
     w_deg = ref_dl.update_dict(w.clone(), x, z_deg)
     save("mstep_degenerate", x=x, weight=w, z=z_deg, weight_update=w_deg, zero_atoms=[3, 17])
 
+    # positive=True: the atom is clamped at zero before it is normalised (dict_learning.py:87-88)
+    w_pos = ref_dl.update_dict(w.clone(), x, z.clone(), positive=True)
+    save("mstep_positive", x=x, weight=w, z=z, weight_update=w_pos)
+
     # ---- convolutional ISTA (lasso/conv2d/ista.py) -------------------------------------
     from lasso.conv2d.ista import ista_conv2d as ref_conv
     g = torch.Generator().manual_seed(77)

@@ -399,6 +399,19 @@ def test_update_dict_large_dictionary_degenerate(dev):
         assert abs(float(got[:, j].norm()) - 1.0) <= 1e-6
 
 
+def test_update_dict_positive(dev):
+    # positive=True (dict_learning.py:87-88) against the reference's own output, on both sweep kernels
+    g = load_golden("mstep_positive")
+    w = update_dict(g["weight"].to(dev).clone(), g["x"].to(dev), g["z"].to(dev).clone(), positive=True)
+    assert rel_fro(w, g["weight_update"]) <= TOL and float(w.min()) >= 0.0
+    n, d, k = 1500, 150, 300          # cluster sweep
+    x, w0 = make_problem(n, d, k, seed=14)
+    z = sparse_encode(x.to(dev), w0.to(dev), alpha=0.1, maxiter=25, tol=0.0)
+    want = oracle.update_dict(w0.clone(), x, z.cpu().clone(), positive=True)
+    got = update_dict(w0.to(dev).clone(), x.to(dev), z.clone(), positive=True)
+    assert rel_fro(got, want) <= TOL and float(got.min()) >= 0.0
+
+
 def test_update_dict_degenerate_atoms(dev):
     g = load_golden("mstep_degenerate")
     zero_atoms = [int(a) for a in g["zero_atoms"]]

@@ -74,6 +74,17 @@ def test_gram_space_sweep_equals_sequential_sweep():
     assert rel_fro(w, g["weight_update"]) <= 5e-6
 
 
+def test_positive_atoms_match_reference():
+    # update_dict(positive=True): atoms clamped at zero before the norm (dict_learning.py:87-88)
+    g = load_golden("mstep_positive")
+    w = oracle.update_dict(g["weight"].clone(), g["x"], g["z"].clone(), positive=True)
+    assert rel_fro(w, g["weight_update"]) <= TOL
+    assert float(g["weight_update"].min()) >= 0.0
+    z64, x64 = g["z"].double(), g["x"].double()
+    w2, zeroed = oracle.update_dict_gram(g["weight"], z64.T @ z64, z64.T @ x64, positive=True)
+    assert zeroed == [] and rel_fro(w2, g["weight_update"]) <= 5e-6
+
+
 def test_degenerate_atoms():
     g = load_golden("mstep_degenerate")
     zero_atoms = [int(a) for a in g["zero_atoms"]]
