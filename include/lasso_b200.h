@@ -111,9 +111,10 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
                                   int32_t path);
 
 /*
- * Convolutional ISTA / FISTA -- replaces the loop of lasso/conv2d/ista.py:7-49 (stride 1,
- * padding 0) as im2col -> linear: rows are the oh x ow patches of every image
- * (oh = h - kh + 1, ow = w - kw + 1), features the cin*kh*kw patch entries, atoms the filters.
+ * Convolutional ISTA / FISTA -- replaces the loop of lasso/conv2d/ista.py:7-49 as
+ * im2col -> linear: rows are the oh x ow patches of every (zero-padded) image
+ * (oh = (h + 2*padding - kh) / stride + 1, ow likewise; both divisions must be exact),
+ * features the cin*kh*kw patch entries, atoms the filters.
  *   conv_transpose2d(z, W) = fold(Z weight_lin^T)   (ista.py:18)
  *   conv2d(r, W)           = unfold(r) weight_lin    (ista.py:19)
  * so every iteration is the first half of the k-blocked tcgen05 kernel (R = Y weight_lin^T),
@@ -127,9 +128,10 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
  */
 int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, const float* z0,
                                     float* z_out, int64_t n_img, int32_t cin, int32_t h, int32_t w,
-                                    int32_t kh, int32_t kw, int32_t k, double alpha, double lr,
-                                    int32_t maxiter, int32_t fast, double tol_abs,
-                                    int32_t* iters_done, double* delta_hist, void* stream);
+                                    int32_t kh, int32_t kw, int32_t stride, int32_t padding,
+                                    int32_t k, double alpha, double lr, int32_t maxiter,
+                                    int32_t fast, double tol_abs, int32_t* iters_done,
+                                    double* delta_hist, void* stream);
 
 /*
  * Lipschitz constant L = lambda_max(W^T W) -- replaces _lipschitz_constant,

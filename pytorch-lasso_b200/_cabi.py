@@ -67,8 +67,8 @@ def _declare(lib):
     lib.lasso_b200_fista_f32_host.argtypes = [vp, vp, vp, vp, i64, i32, i32, f64, f64, i32,
                                               i32, f64, c.POINTER(i32), vp, i32]
     lib.lasso_b200_conv2d_fista_f32.restype = i32
-    lib.lasso_b200_conv2d_fista_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f64, f64,
-                                                i32, i32, f64, c.POINTER(i32), vp, vp]
+    lib.lasso_b200_conv2d_fista_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32,
+                                                f64, f64, i32, i32, f64, c.POINTER(i32), vp, vp]
     lib.lasso_b200_lipschitz_f32.restype = i32
     lib.lasso_b200_lipschitz_f32.argtypes = [vp, i32, i32, i32, c.POINTER(f64), vp]
     lib.lasso_b200_loss_terms_f32.restype = i32
@@ -167,15 +167,16 @@ def fista_device(x, weight, z0, alpha, lr, maxiter, fast, tol_abs, path=PATH_AUT
     return z, (iters.value if want_iters else None), (hist[:maxiter] if want_hist else None)
 
 
-def conv2d_fista_device(x, weight_lin, z0_rows, kh, kw, alpha, lr, maxiter, fast, tol_abs, want_iters=False):
+def conv2d_fista_device(x, weight_lin, z0_rows, kh, kw, alpha, lr, maxiter, fast, tol_abs, want_iters=False,
+                        stride=1, padding=0):
     """Convolutional FISTA on device tensors: x [n,cin,h,w], weight_lin [cin*kh*kw, k], codes as rows
-    [n*oh*ow, k].  Returns (z_rows, iters_done|None)."""
+    [n*oh*ow, k] with oh = (h + 2*padding - kh) // stride + 1.  Returns (z_rows, iters_done|None)."""
     lib = load()
     x = _dev_f32(x, "x")
     weight_lin = _dev_f32(weight_lin, "weight_lin")
     n_img, cin, h, w = x.shape
     k = weight_lin.shape[1]
-    rows = n_img * (h - kh + 1) * (w - kw + 1)
+    rows = n_img * ((h + 2 * padding - kh) // stride + 1) * ((w + 2 * padding - kw) // stride + 1)
     if z0_rows is not None:
         z0_rows = _dev_f32(z0_rows, "z0")
     z = torch.empty((rows, k), dtype=torch.float32, device=x.device)
@@ -183,7 +184,8 @@ def conv2d_fista_device(x, weight_lin, z0_rows, kh, kw, alpha, lr, maxiter, fast
     with torch.cuda.device(x.device):
         _check(lib.lasso_b200_conv2d_fista_f32(
             x.data_ptr(), weight_lin.data_ptr(), z0_rows.data_ptr() if z0_rows is not None else None,
-            z.data_ptr(), n_img, cin, h, w, int(kh), int(kw), k, float(alpha), float(lr), int(maxiter),
+            z.data_ptr(), n_img, cin, h, w, int(kh), int(kw), int(stride), int(padding), k, float(alpha),
+            float(lr), int(maxiter),
             int(bool(fast)), float(tol_abs), ctypes.byref(iters) if want_iters else None, None,
             _stream_ptr(x.device)))
     return z, (iters.value if want_iters else None)

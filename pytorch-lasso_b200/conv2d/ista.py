@@ -7,7 +7,8 @@ im2col -> linear on the k-blocked tcgen05 kernel (``lasso_b200_conv2d_fista_f32`
 iteration.  Codes keep the reference's layout ``[n, filters, oh, ow]`` at the boundary; inside
 they are patch-major rows ``[n*oh*ow, filters]`` (two permutes per call).
 
-Built: ``stride=1``, ``padding=0``, ``cin*kh*kw <= 128``, ``filters <= 1024`` (multiples of 4).
+Built: any integer ``stride`` / ``padding`` (the same for both axes), ``cin*kh*kw <= 128``,
+``filters <= 1024`` (multiples of 4), one image's patch matrix within 200 KB of shared memory.
 Everything else raises -- there is no PyTorch fallback.
 """
 from __future__ import annotations
@@ -29,8 +30,8 @@ def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
             raise NotImplementedError("auto lr is only implemented for "
                                       "stride == 1.")          # ista.py:10-12
         lr = 1 / float(lip_bound_conv2d(weight, padding))      # ista.py:13-15 (odd kernels only)
-    if stride != 1 or padding != 0:
-        raise NotImplementedError("lasso_b200.conv2d is built for stride=1, padding=0")
+    if not (isinstance(stride, int) and isinstance(padding, int)) or stride < 1 or padding < 0:
+        raise NotImplementedError("lasso_b200.conv2d takes one integer stride >= 1 and padding >= 0 for both axes")
     if verbose:
         raise NotImplementedError("verbose=True is not built for the convolutional path")
     for name, t in (("x", x), ("z0", z0), ("weight", weight)):
@@ -42,7 +43,10 @@ def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
         return z0
     filters, cin, kh, kw = weight.shape
     n, cx, h, w = x.shape
-    oh, ow = h - kh + 1, w - kw + 1
+    if (h + 2 * padding - kh) % stride or (w + 2 * padding - kw) % stride:
+        # conv_transpose2d(z) would come out smaller than x: the reference fails on `x_hat - x` (ista.py:18-19)
+        raise RuntimeError("image size + 2*padding - kernel size must be a multiple of stride={}".format(stride))
+    oh, ow = (h + 2 * padding - kh) // stride + 1, (w + 2 * padding - kw) // stride + 1
     if cx != cin or tuple(z0.shape) != (n, filters, oh, ow):
         raise ValueError("expected x[n,{},h,w] and z0[n,{},{},{}]; got {} and {}".format(
             cin, filters, oh, ow, tuple(x.shape), tuple(z0.shape)))
@@ -54,6 +58,6 @@ def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
     if not bool(z_rows.any()):
         z_rows = None                                          # zero start: the kernel clears its own buffer
     out_rows, _ = _cabi.conv2d_fista_device(x.to(dev).contiguous(), w_lin, z_rows, kh, kw, alpha, float(lr),
-                                            maxiter, fast, tol_abs)
+                                            maxiter, fast, tol_abs, stride=stride, padding=padding)
     z = out_rows.reshape(n, oh, ow, filters).permute(0, 3, 1, 2).contiguous()
     return z if x.is_cuda else z.cpu()

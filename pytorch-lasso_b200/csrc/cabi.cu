@@ -320,11 +320,12 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
 
 int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, const float* z0, float* z_out,
                                     int64_t n_img, int32_t cin, int32_t h, int32_t w, int32_t kh, int32_t kw,
-                                    int32_t k, double alpha, double lr, int32_t maxiter, int32_t fast,
-                                    double tol_abs, int32_t* iters_done, double* delta_hist, void* stream) {
+                                    int32_t stride, int32_t padding, int32_t k, double alpha, double lr,
+                                    int32_t maxiter, int32_t fast, double tol_abs, int32_t* iters_done,
+                                    double* delta_hist, void* stream) {
   t_error[0] = 0;
-  if (n_img < 0 || cin <= 0 || kh <= 0 || kw <= 0 || h < kh || w < kw || k <= 0 || !weight_lin ||
-      (n_img > 0 && (!x || !z_out))) {
+  if (n_img < 0 || cin <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || padding < 0 || h + 2 * padding < kh ||
+      w + 2 * padding < kw || k <= 0 || !weight_lin || (n_img > 0 && (!x || !z_out))) {
     set_error("invalid argument to conv2d_fista");
     return LASSO_B200_ERR_INVALID;
   }
@@ -336,11 +337,18 @@ int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, con
     if (iters_done) *iters_done = 0;
     return LASSO_B200_OK;
   }
-  const int64_t P = (int64_t)(h - kh + 1) * (w - kw + 1), n = n_img * P;
+  ConvShape shape{n_img, cin, h, w, kh, kw, stride, padding};
+  if ((h + 2 * padding - kh) % stride != 0 || (w + 2 * padding - kw) % stride != 0) {
+    // conv_transpose2d of the codes would be smaller than x (the reference fails on `x_hat - x`)
+    set_error("conv2d_fista: (h + 2*padding - kh) and (w + 2*padding - kw) must be multiples of stride=%d", stride);
+    return LASSO_B200_ERR_INVALID;
+  }
+  const int64_t P = (int64_t)shape.oh() * shape.ow(), n = n_img * P;
   const int d = cin * kh * kw;
-  if (!conv2d_blk_supported(n_img, cin, h, w, kh, kw, k)) {
+  if (!conv2d_blk_supported(shape, k)) {
     set_error("conv2d path needs cin*kh*kw <= 128 (multiple of 4), filters <= 1024 (multiple of 4) and one image's "
-              "patch matrix within 200 KB; got cin=%d %dx%d kernel, %d filters, %dx%d images", cin, kh, kw, k, h, w);
+              "patch matrix within 200 KB; got cin=%d %dx%d kernel, %d filters, %dx%d images, stride %d, padding %d",
+              cin, kh, kw, k, h, w, stride, padding);
     return LASSO_B200_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -380,7 +388,6 @@ int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, con
   a.tol_abs = tol_abs;
   a.hist = hist;
   a.zero_start = z0 == nullptr ? 1 : 0;
-  ConvShape shape{n_img, cin, h, w, kh, kw};
   int fell_back = 0;
   if ((rc = fista_blk_run(a, &fell_back, st, &shape))) return rc;
   if (fell_back) {

@@ -112,9 +112,14 @@ int fista_ffma_run(const FistaArgs& a, float* z_out, cudaStream_t st);
 struct ConvShape {
   int64_t n_img;
   int cin, h, w, kh, kw;
+  int stride, pad;
+  // code grid of conv2d(x, W, stride, padding): (h + 2 pad - kh) / stride + 1 (exact division, else
+  // conv_transpose2d of the codes would not reproduce x's size)
+  __host__ __device__ int oh() const { return (h + 2 * pad - kh) / stride + 1; }
+  __host__ __device__ int ow() const { return (w + 2 * pad - kw) / stride + 1; }
 };
 bool fista_blk_supported(int64_t n, int d, int k);
-bool conv2d_blk_supported(int64_t n_img, int cin, int h, int w, int kh, int kw, int k);
+bool conv2d_blk_supported(const ConvShape& c, int k);
 int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const ConvShape* conv = nullptr);
 bool fista_res_supported(int64_t n, int d, int k);
 int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int iters, int fast,

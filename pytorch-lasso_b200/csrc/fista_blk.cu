@@ -575,13 +575,17 @@ __global__ void __launch_bounds__(256) conv_scale_kernel(const float* __restrict
   }
 }
 
-// r = unfold(fold(R) - sx x), in place on the [P][d] block of one image; one CTA per image
+// r = unfold(fold(R) - sx x), in place on the [P][d] block of one image; one CTA per image.
+// Patch (pi, pj) covers the pixels (stride pi + a - pad, stride pj + b - pad): conv_transpose2d crops the
+// `pad` border of the overlap-add and conv2d pads the residual with zeros, so border entries of a patch
+// that fall outside the image contribute nothing and read back as zero (conv2d/ista.py:18-19).
 __global__ void __launch_bounds__(512) conv_resid_kernel(float* __restrict__ rbuf, const float* __restrict__ x,
-                                                         const float* __restrict__ row_scale, int cin, int H, int W,
-                                                         int kh, int kw, StepCtl ctl) {
+                                                         const float* __restrict__ row_scale, ConvShape cs,
+                                                         StepCtl ctl) {
   extern __shared__ __align__(16) float conv_smem[];
   if (ctl.tol_abs >= 0.0 && ctl.iter >= 1 && ctl.hist[ctl.iter - 1] <= ctl.tol_abs) return;
-  const int oh = H - kh + 1, ow = W - kw + 1, P = oh * ow, kk = kh * kw, d = cin * kk;
+  const int cin = cs.cin, H = cs.h, W = cs.w, kh = cs.kh, kw = cs.kw, st = cs.stride, pad = cs.pad;
+  const int oh = cs.oh(), ow = cs.ow(), P = oh * ow, kk = kh * kw, d = cin * kk;
   float* Rs = conv_smem;              // [P][d]
   float* img = conv_smem + P * d;     // [cin][H][W]
   const int64_t i_img = blockIdx.x;
@@ -595,12 +599,13 @@ __global__ void __launch_bounds__(512) conv_resid_kernel(float* __restrict__ rbu
     const int c = pix / (H * W), i = (pix / W) % H, j = pix % W;
     float acc = 0.f;
     for (int a = 0; a < kh; ++a) {
-      const int pi = i - a;
-      if (pi < 0 || pi >= oh) continue;
+      const int ti = i + pad - a;
+      if (ti < 0 || (ti % st) != 0 || ti / st >= oh) continue;
+      const int pi = ti / st;
       for (int b = 0; b < kw; ++b) {
-        const int pj = j - b;
-        if (pj < 0 || pj >= ow) continue;
-        acc += Rs[(pi * ow + pj) * d + c * kk + a * kw + b];
+        const int tj = j + pad - b;
+        if (tj < 0 || (tj % st) != 0 || tj / st >= ow) continue;
+        acc += Rs[(pi * ow + tj / st) * d + c * kk + a * kw + b];
       }
     }
     img[pix] = acc - sx * x[i_img * (int64_t)(cin * H * W) + pix];
@@ -609,8 +614,8 @@ __global__ void __launch_bounds__(512) conv_resid_kernel(float* __restrict__ rbu
   for (int e = tid; e < P * d; e += blockDim.x) {
     const int pch = e / d, f = e % d;
     const int c = f / kk, a = (f / kw) % kh, b = f % kw;
-    const int pi = pch / ow, pj = pch % ow;
-    rb[e] = img[c * H * W + (pi + a) * W + pj + b];
+    const int i = (pch / ow) * st + a - pad, j = (pch % ow) * st + b - pad;
+    rb[e] = (i >= 0 && i < H && j >= 0 && j < W) ? img[c * H * W + i * W + j] : 0.f;
   }
 }
 
@@ -668,11 +673,14 @@ bool fista_blk_supported(int64_t n, int d, int k) {
          n < ((int64_t)1 << 31) - kTileM;
 }
 
-bool conv2d_blk_supported(int64_t n_img, int cin, int h, int w, int kh, int kw, int k) {
-  if (n_img < 1 || cin < 1 || kh < 1 || kw < 1 || h < kh || w < kw) return false;
-  const int64_t P = (int64_t)(h - kh + 1) * (w - kw + 1);
-  const int d = cin * kh * kw;
-  return fista_blk_supported(n_img * P, d, k) && (size_t)(P * d + (int64_t)cin * h * w) * sizeof(float) <= 200 * 1024;
+bool conv2d_blk_supported(const ConvShape& c, int k) {
+  if (c.n_img < 1 || c.cin < 1 || c.kh < 1 || c.kw < 1 || c.stride < 1 || c.pad < 0 || c.h + 2 * c.pad < c.kh ||
+      c.w + 2 * c.pad < c.kw || (c.h + 2 * c.pad - c.kh) % c.stride != 0 || (c.w + 2 * c.pad - c.kw) % c.stride != 0)
+    return false;
+  const int64_t P = (int64_t)c.oh() * c.ow();
+  const int d = c.cin * c.kh * c.kw;
+  return fista_blk_supported(c.n_img * P, d, k) &&
+         (size_t)(P * d + (int64_t)c.cin * c.h * c.w) * sizeof(float) <= 200 * 1024;
 }
 
 // Same contract as fista_tc_run: z_i lives in (i even ? z_a : z_b).  *fell_back = 1 when an
@@ -714,7 +722,7 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
   int conv_P = 0;
   size_t conv_smem = 0;
   if (conv) {
-    conv_P = (conv->h - conv->kh + 1) * (conv->w - conv->kw + 1);
+    conv_P = conv->oh() * conv->ow();
     conv_smem = ((size_t)conv_P * a.d + (size_t)conv->cin * conv->h * conv->w) * sizeof(float);
     const size_t need = sizeof(float) * (size_t)a.n * a.d;
     if (need > S.r_cap) {
@@ -786,8 +794,7 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
       LASSO_CHECK_LAUNCH();
       count_launch();
       if (conv && half == 0) {
-        conv_resid_kernel<<<(unsigned)conv->n_img, 512, conv_smem, st>>>(S.r_buf, a.x, S.row_scale, conv->cin, conv->h,
-                                                                         conv->w, conv->kh, conv->kw, p.ctl);
+        conv_resid_kernel<<<(unsigned)conv->n_img, 512, conv_smem, st>>>(S.r_buf, a.x, S.row_scale, *conv, p.ctl);
         LASSO_CHECK_LAUNCH();
         count_launch();
       }

@@ -42,7 +42,8 @@ SOLVER_CASES = [
 ]
 
 
-CONV_CASES = ["conv_8x8_fista", "conv_8x8_plain", "conv_8x8_warmstart", "conv_3x3_auto_earlystop"]
+CONV_CASES = ["conv_8x8_fista", "conv_8x8_plain", "conv_8x8_warmstart", "conv_3x3_auto_earlystop",
+              "conv_8x8_pad3", "conv_4x4_stride2", "conv_4x4_stride2_pad1", "conv_3x3_pad1_auto"]
 
 
 @pytest.fixture(scope="session")

@@ -163,6 +163,32 @@ def main():
     save("conv_3x3_auto_earlystop", x=x, weight=w, z0=z0, z=z, alpha=0.1, lr=-1.0, fast=1, maxiter=300,
          tol=1e-3, lip_bound=float(ref_bound(w, 0)))
 
+    # stride / padding (ista.py:7, 18-19): patches of the zero-padded image on a stride grid
+    def conv_problem_sp(n, cin, size, filters, ksize, stride, padding, density=0.05):
+        w = torch.randn(filters, cin, ksize, ksize, generator=g)
+        w = w / w.flatten(1).norm(dim=1).view(-1, 1, 1, 1)
+        o = (size + 2 * padding - ksize) // stride + 1
+        code = torch.randn(n, filters, o, o, generator=g) * (torch.rand(n, filters, o, o, generator=g) < density)
+        x = torch.nn.functional.conv_transpose2d(code, w, stride=stride, padding=padding)
+        assert x.shape[-1] == size
+        return x + 0.01 * torch.randn(n, cin, size, size, generator=g), w, o
+
+    for name, (cin, size, filters, ksize, stride, padding, fast, iters) in {
+            "conv_8x8_pad3": (1, 20, 16, 8, 1, 3, True, 20),
+            "conv_4x4_stride2": (4, 20, 16, 4, 2, 0, True, 20),
+            "conv_4x4_stride2_pad1": (4, 20, 16, 4, 2, 1, False, 12)}.items():
+        x, w, o = conv_problem_sp(4, cin, size, filters, ksize, stride, padding)
+        lr = conv_lr(w) * 4
+        z0 = torch.zeros(4, filters, o, o)
+        z = ref_conv(x, z0, w, alpha=0.05, stride=stride, padding=padding, fast=fast, maxiter=iters, lr=lr, tol=0.0)
+        save(name, x=x, weight=w, z0=z0, z=z, alpha=0.05, lr=lr, fast=int(fast), maxiter=iters, tol=0.0,
+             stride=stride, padding=padding)
+    x, w, o = conv_problem_sp(4, 4, 12, 12, 3, 1, 1)
+    z0 = torch.zeros(4, 12, o, o)
+    z = ref_conv(x, z0, w, alpha=0.1, stride=1, padding=1, fast=True, maxiter=40, lr='auto', tol=0.0)
+    save("conv_3x3_pad1_auto", x=x, weight=w, z0=z0, z=z, alpha=0.1, lr=-1.0, fast=1, maxiter=40, tol=0.0,
+         stride=1, padding=1, lip_bound=float(ref_bound(w, 1)))
+
     for constrained in (True, False):
         x, _ = make_problem(128, 10, 50, seed=21, kind="randn")
         torch.manual_seed(0)

@@ -492,8 +492,9 @@ def test_conv2d_ista_matches_reference(dev, name):
     from lasso_b200.conv2d import ista_conv2d
     g = load_golden(name)
     lr = "auto" if g["lr"] < 0 else g["lr"]
-    z = ista_conv2d(g["x"].to(dev), g["z0"].to(dev), g["weight"].to(dev), alpha=g["alpha"],
-                    fast=bool(g["fast"]), maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
+    stride, padding = int(g.get("stride", 1)), int(g.get("padding", 0))
+    z = ista_conv2d(g["x"].to(dev), g["z0"].to(dev), g["weight"].to(dev), alpha=g["alpha"], stride=stride,
+                    padding=padding, fast=bool(g["fast"]), maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
     assert z.shape == g["z"].shape and z.is_cuda
     assert rel_fro(z, g["z"]) <= TOL
     assert support_mismatch(z.cpu(), g["z"]) <= 2e-3

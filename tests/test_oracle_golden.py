@@ -124,12 +124,13 @@ def test_conv2d_ista_matches_reference(name):
     from lasso_b200.conv2d import lip_bound_conv2d
     g = load_golden(name)
     lr = g["lr"]
+    stride, padding = int(g.get("stride", 1)), int(g.get("padding", 0))
     if lr < 0:      # the case was generated with lr='auto': the Fourier bound must match the reference's
-        bound = float(lip_bound_conv2d(g["weight"], 0))
+        bound = float(lip_bound_conv2d(g["weight"], padding))
         assert abs(bound - g["lip_bound"]) <= 1e-6 * g["lip_bound"]
         lr = 1 / bound
-    z = oracle.conv2d_ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=bool(g["fast"]),
-                           maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
+    z = oracle.conv2d_ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], stride=stride, padding=padding,
+                           fast=bool(g["fast"]), maxiter=int(g["maxiter"]), lr=lr, tol=g["tol"])
     assert rel_fro(z, g["z"]) <= TOL
 
 
