@@ -579,43 +579,87 @@ __global__ void __launch_bounds__(256) conv_scale_kernel(const float* __restrict
 // Patch (pi, pj) covers the pixels (stride pi + a - pad, stride pj + b - pad): conv_transpose2d crops the
 // `pad` border of the overlap-add and conv2d pads the residual with zeros, so border entries of a patch
 // that fall outside the image contribute nothing and read back as zero (conv2d/ista.py:18-19).
-__global__ void __launch_bounds__(512) conv_resid_kernel(float* __restrict__ rbuf, const float* __restrict__ x,
-                                                         const float* __restrict__ row_scale, ConvShape cs,
-                                                         StepCtl ctl) {
+// Shared-memory rows of R are d + 1 floats apart: in the overlap-add neighbouring threads read
+// neighbouring patches (a stride of d floats would put a whole warp on one bank).  blockDim.x is a
+// multiple of d, so a thread keeps its feature (c, a, b) and walks the patches without divisions.
+__host__ __device__ inline int conv_row_ld(int d) { return d | 1; }
+template <bool kUnitStride>
+__global__ void __launch_bounds__(1024) conv_resid_kernel(float* __restrict__ rbuf, const float* __restrict__ x,
+                                                          const float* __restrict__ row_scale, ConvShape cs,
+                                                          StepCtl ctl) {
   extern __shared__ __align__(16) float conv_smem[];
   if (ctl.tol_abs >= 0.0 && ctl.iter >= 1 && ctl.hist[ctl.iter - 1] <= ctl.tol_abs) return;
   const int cin = cs.cin, H = cs.h, W = cs.w, kh = cs.kh, kw = cs.kw, st = cs.stride, pad = cs.pad;
-  const int oh = cs.oh(), ow = cs.ow(), P = oh * ow, kk = kh * kw, d = cin * kk;
-  float* Rs = conv_smem;              // [P][d]
-  float* img = conv_smem + P * d;     // [cin][H][W]
+  const int oh = cs.oh(), ow = cs.ow(), P = oh * ow, kk = kh * kw, d = cin * kk, ld = conv_row_ld(d);
+  float* Rs = conv_smem;              // [P][ld]
+  float* img = conv_smem + P * ld;    // [cin][H][W]
   const int64_t i_img = blockIdx.x;
   float* rb = rbuf + i_img * (int64_t)P * d;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < (P * d) / 4; e += blockDim.x)
-    reinterpret_cast<float4*>(Rs)[e] = reinterpret_cast<const float4*>(rb)[e];
-  const float sx = row_scale[i_img * P];
-  __syncthreads();
-  for (int pix = tid; pix < cin * H * W; pix += blockDim.x) {
-    const int c = pix / (H * W), i = (pix / W) % H, j = pix % W;
-    float acc = 0.f;
-    for (int a = 0; a < kh; ++a) {
-      const int ti = i + pad - a;
-      if (ti < 0 || (ti % st) != 0 || ti / st >= oh) continue;
-      const int pi = ti / st;
-      for (int b = 0; b < kw; ++b) {
-        const int tj = j + pad - b;
-        if (tj < 0 || (tj % st) != 0 || tj / st >= ow) continue;
-        acc += Rs[(pi * ow + tj / st) * d + c * kk + a * kw + b];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int f = tid % d, grp = tid / d, ngrp = nthr / d;     // this thread's feature, its first patch
+  {
+    // d % 4 == 0: float4 loads (eight in flight per thread), scalar stores into the padded rows
+    const int q4 = d >> 2, total = P * q4;
+    for (int e0 = 0; e0 < total; e0 += 8 * nthr) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * nthr + tid;
+        if (e < total) v[u] = __ldcs(reinterpret_cast<const float4*>(rb) + e);   // (rewritten below: no .nc load)
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * nthr + tid;
+        if (e < total) {
+          float* dst = Rs + (e / q4) * ld + (e % q4) * 4;
+          dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+        }
       }
     }
-    img[pix] = acc - sx * x[i_img * (int64_t)(cin * H * W) + pix];
+  }
+  const float sx = row_scale[i_img * P];
+  __syncthreads();
+  for (int pix = tid; pix < cin * H * W; pix += nthr) {
+    const int c = pix / (H * W), i = (pix / W) % H, j = pix % W;
+    float acc = 0.f;
+    if (kUnitStride) {
+      // patches (i + pad - a, j + pad - b) inside the code grid: contiguous ranges of a and b, no tests inside
+      const int a_lo = max(0, i + pad - (oh - 1)), a_hi = min(kh - 1, i + pad);
+      const int b_lo = max(0, j + pad - (ow - 1)), b_hi = min(kw - 1, j + pad);
+      for (int a = a_lo; a <= a_hi; ++a) {
+        const float* rrow = Rs + ((i + pad - a) * ow + (j + pad)) * ld + c * kk + a * kw;
+        for (int b = b_lo; b <= b_hi; ++b) acc += rrow[b - b * ld];
+      }
+    } else {
+      for (int a = 0; a < kh; ++a) {
+        const int ti = i + pad - a;
+        if (ti < 0 || (ti % st) != 0 || ti / st >= oh) continue;
+        const float* rrow = Rs + (ti / st) * ow * ld + c * kk + a * kw;
+        for (int b = 0; b < kw; ++b) {
+          const int tj = j + pad - b;
+          if (tj < 0 || (tj % st) != 0 || tj / st >= ow) continue;
+          acc += rrow[(tj / st) * ld + b];
+        }
+      }
+    }
+    img[pix] = acc - sx * __ldg(x + i_img * (int64_t)(cin * H * W) + pix);
   }
   __syncthreads();
-  for (int e = tid; e < P * d; e += blockDim.x) {
-    const int pch = e / d, f = e % d;
+  {
     const int c = f / kk, a = (f / kw) % kh, b = f % kw;
-    const int i = (pch / ow) * st + a - pad, j = (pch % ow) * st + b - pad;
-    rb[e] = (i >= 0 && i < H && j >= 0 && j < W) ? img[c * H * W + i * W + j] : 0.f;
+    const float* ibase = img + c * H * W;
+    int pi = grp / ow, pj = grp % ow;
+    const int dpi = ngrp / ow, dpj = ngrp % ow;
+    for (int pch = grp; pch < P; pch += ngrp) {
+      const int i = pi * st + a - pad, j = pj * st + b - pad;
+      rb[(int64_t)pch * d + f] = (i >= 0 && i < H && j >= 0 && j < W) ? ibase[i * W + j] : 0.f;
+      pi += dpi;
+      pj += dpj;
+      if (pj >= ow) {
+        pj -= ow;
+        ++pi;
+      }
+    }
   }
 }
 
@@ -680,7 +724,7 @@ bool conv2d_blk_supported(const ConvShape& c, int k) {
   const int64_t P = (int64_t)c.oh() * c.ow();
   const int d = c.cin * c.kh * c.kw;
   return fista_blk_supported(c.n_img * P, d, k) &&
-         (size_t)(P * d + (int64_t)c.cin * c.h * c.w) * sizeof(float) <= 200 * 1024;
+         (size_t)(P * (d | 1) + (int64_t)c.cin * c.h * c.w) * sizeof(float) <= 200 * 1024;   // conv_row_ld(d)
 }
 
 // Same contract as fista_tc_run: z_i lives in (i even ? z_a : z_b).  *fell_back = 1 when an
@@ -723,7 +767,7 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
   size_t conv_smem = 0;
   if (conv) {
     conv_P = conv->oh() * conv->ow();
-    conv_smem = ((size_t)conv_P * a.d + (size_t)conv->cin * conv->h * conv->w) * sizeof(float);
+    conv_smem = ((size_t)conv_P * conv_row_ld(a.d) + (size_t)conv->cin * conv->h * conv->w) * sizeof(float);
     const size_t need = sizeof(float) * (size_t)a.n * a.d;
     if (need > S.r_cap) {
       if (S.r_buf) LASSO_CUDA_TRY(cudaFree(S.r_buf));
@@ -733,8 +777,10 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
       S.r_cap = need;
     }
     if (!S.conv_attr_set) {
-      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)conv_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
+      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)conv_resid_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)conv_resid_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       S.conv_attr_set = true;
     }
     conv_scale_kernel<<<(unsigned)conv->n_img, 256, 0, st>>>(a.x, conv->cin * conv->h * conv->w, conv_P, a.k, S.scal,
@@ -794,7 +840,12 @@ int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const Con
       LASSO_CHECK_LAUNCH();
       count_launch();
       if (conv && half == 0) {
-        conv_resid_kernel<<<(unsigned)conv->n_img, 512, conv_smem, st>>>(S.r_buf, a.x, S.row_scale, *conv, p.ctl);
+        if (conv->stride == 1)
+          conv_resid_kernel<true><<<(unsigned)conv->n_img, (1024 / a.d) * a.d, conv_smem, st>>>(S.r_buf, a.x, S.row_scale,
+                                                                                               *conv, p.ctl);
+        else
+          conv_resid_kernel<false><<<(unsigned)conv->n_img, (1024 / a.d) * a.d, conv_smem, st>>>(S.r_buf, a.x, S.row_scale,
+                                                                                                *conv, p.ctl);
         LASSO_CHECK_LAUNCH();
         count_launch();
       }
