@@ -143,3 +143,11 @@ def test_conv2d_lip_bound_error_behaviour():
         lip_bound_conv2d(torch.randn(4, 1, 3, 5), 0)
     with pytest.raises(NotImplementedError):             # ista.py:10-12
         ista_conv2d(torch.randn(1, 1, 9, 9), torch.zeros(1, 4, 4, 4), torch.randn(4, 1, 3, 3), stride=2)
+    # (h + 2 padding - kh) not a multiple of the stride: conv_transpose2d(z) cannot have x's size (the reference
+    # fails on `x_hat - x`, ista.py:18-19); a code tensor of the wrong grid is a ValueError before any GPU work
+    with pytest.raises(RuntimeError):
+        ista_conv2d(torch.randn(1, 1, 10, 10), torch.zeros(1, 4, 4, 4), torch.randn(4, 1, 3, 3), stride=2, lr=0.1)
+    with pytest.raises(ValueError):
+        ista_conv2d(torch.randn(1, 1, 9, 9), torch.zeros(1, 4, 7, 7), torch.randn(4, 1, 3, 3), stride=2, lr=0.1)
+    z0 = torch.zeros(1, 4, 4, 4)
+    assert ista_conv2d(torch.randn(1, 1, 9, 9), z0, torch.randn(4, 1, 3, 3), stride=2, lr=0.1, maxiter=0) is z0
