@@ -72,25 +72,30 @@ struct StepParams {
 // MODE 2 = gradient: z_io <- (z_cur W^T - x) W, out2[0] += sum r^2            (ista.py:22-24)
 // MODE 3 = line-search trial: cand = softshrink(z_cur - lr * aux, lam) -> out,  (ista.py:40)
 //          out2 += { sum (cand W^T - x)^2, sum |cand|, sum dz * aux, sum dz^2 } (ista.py:26-35)
-template <int TM, int MODE>
-__global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(StepParams p) {
+// BLK = width of an output block (d-block in phase 1, atom chunk in phase 2); BLK * 4 threads, each a
+// (TM / 16) x 4 register tile.  BLK = 128 (512 threads) halves the number of block steps of a tile (tuning
+// variant, see use_wide_blocks).
+template <int TM, int MODE, int BLK>
+__global__ void __launch_bounds__(BLK * 4, BLK == 128 ? 1 : (TM == 64 ? 2 : 3)) fista_ffma_kernel(StepParams p) {
+  constexpr int NT = BLK * 4;     // threads
+  constexpr int CT = BLK / 4;     // threads across an output block (4 columns each)
   constexpr int RPT = TM / 16;  // rows per thread
-  constexpr int A_IT = (TM * (kCk / 4) + kThreads - 1) / kThreads;   // float4 per thread of a Y chunk
-  constexpr int W_IT = kBlk * (kCk / 4) / kThreads;                  // float4 per thread of a W chunk
+  constexpr int A_IT = (TM * (kCk / 4) + NT - 1) / NT;   // float4 per thread of a Y chunk
+  constexpr int W_IT = BLK * (kCk / 4) / NT;                  // float4 per thread of a W chunk
   extern __shared__ __align__(16) float smem[];
   const int d_pad = (p.d + 3) & ~3;
   const int r_ld = d_pad + kPad;
   float* Rs = smem;                                   // [TM][r_ld]
   float* As = Rs + TM * r_ld;                         // [TM][kCk + kPad]   (Y chunk)
-  float* Ws = As + TM * (kCk + kPad);                 // max([kBlk][kCk+kPad], [kCk][kBlk+kPad])
-  __shared__ double red[kThreads / 32][4];
+  float* Ws = As + TM * (kCk + kPad);                 // max([BLK][kCk+kPad], [kCk][BLK+kPad])
+  __shared__ double red[NT / 32][4];
 
   if (MODE == 0 && p.ctl.tol_abs >= 0.0 && p.ctl.iter >= 1 &&
       p.ctl.hist[p.ctl.iter - 1] <= p.ctl.tol_abs)
     return;  // an earlier iteration met the stop test (ista.py:93-95)
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid % CT, ty = tid / CT;
   const bool kvec = (p.k & 3) == 0;
   const bool dvec = (p.d & 3) == 0;
   const int64_t ntiles = (p.n + TM - 1) / TM;
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
     auto fetch1 = [&](int db, int j0) {
 #pragma unroll
       for (int it = 0; it < A_IT; ++it) {
-        const int e = tid + it * kThreads;
+        const int e = tid + it * NT;
         if (e < TM * (kCk / 4)) {
           const int r = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
           ra[it] = ld4(p.z_cur, row0 + r, j0 + c4, p.n, p.k, p.k, kvec);
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
       }
 #pragma unroll
       for (int it = 0; it < W_IT; ++it) {
-        const int e = tid + it * kThreads;
+        const int e = tid + it * NT;
         const int i = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
         rw[it] = ld4(p.w, db + i, j0 + c4, p.d, p.k, p.k, kvec);
       }
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
     auto commit1 = [&](int db, int j0) {
 #pragma unroll
       for (int it = 0; it < A_IT; ++it) {
-        const int e = tid + it * kThreads;
+        const int e = tid + it * NT;
         if (e < TM * (kCk / 4)) {
           const int r = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
           float4 zc = ra[it];
@@ -160,12 +165,12 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
       }
 #pragma unroll
       for (int it = 0; it < W_IT; ++it) {
-        const int e = tid + it * kThreads;
+        const int e = tid + it * NT;
         const int i = e / (kCk / 4), c4 = (e % (kCk / 4)) * 4;
         *reinterpret_cast<float4*>(&Ws[i * (kCk + kPad) + c4]) = rw[it];
       }
     };
-    for (int db = 0; db < p.d; db += kBlk) {
+    for (int db = 0; db < p.d; db += BLK) {
       float acc[RPT][4];
 #pragma unroll
       for (int r = 0; r < RPT; ++r)
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
             a[r] = *reinterpret_cast<const float4*>(&As[(ty * RPT + r) * (kCk + kPad) + jj]);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            b[c] = *reinterpret_cast<const float4*>(&Ws[(tx + 16 * c) * (kCk + kPad) + jj]);
+            b[c] = *reinterpret_cast<const float4*>(&Ws[(tx + CT * c) * (kCk + kPad) + jj]);
 #pragma unroll
           for (int r = 0; r < RPT; ++r)
 #pragma unroll
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
       for (int r = 0; r < RPT; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int lr_ = ty * RPT + r, i = db + tx + 16 * c;
+          const int lr_ = ty * RPT + r, i = db + tx + CT * c;
           const int64_t gr = row0 + lr_;
           float v = 0.f;
           if (gr < p.n && i < p.d) v = __fsub_rn(acc[r][c], p.x[gr * p.d + i]);
@@ -214,23 +219,23 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
     if (MODE == 1 || MODE == 3) continue;
 
     // ---------------- phase 2: G = R W, fused update ----------------------
-    auto fetch2 = [&](int j0, int i0) {   // W chunk [kCk][kBlk] (output-contiguous), one step ahead
+    auto fetch2 = [&](int j0, int i0) {   // W chunk [kCk][BLK] (output-contiguous), one step ahead
 #pragma unroll
       for (int it = 0; it < W_IT; ++it) {
-        const int e = tid + it * kThreads;
-        const int ii = e / (kBlk / 4), c4 = (e % (kBlk / 4)) * 4;
+        const int e = tid + it * NT;
+        const int ii = e / (BLK / 4), c4 = (e % (BLK / 4)) * 4;
         rw[it] = ld4(p.w, i0 + ii, j0 + c4, p.d, p.k, p.k, kvec);
       }
     };
     auto commit2 = [&]() {
 #pragma unroll
       for (int it = 0; it < W_IT; ++it) {
-        const int e = tid + it * kThreads;
-        const int ii = e / (kBlk / 4), c4 = (e % (kBlk / 4)) * 4;
-        *reinterpret_cast<float4*>(&Ws[ii * (kBlk + kPad) + c4]) = rw[it];
+        const int e = tid + it * NT;
+        const int ii = e / (BLK / 4), c4 = (e % (BLK / 4)) * 4;
+        *reinterpret_cast<float4*>(&Ws[ii * (BLK + kPad) + c4]) = rw[it];
       }
     };
-    for (int j0 = 0; j0 < p.k; j0 += kBlk) {
+    for (int j0 = 0; j0 < p.k; j0 += BLK) {
       float acc[RPT][4];
 #pragma unroll
       for (int r = 0; r < RPT; ++r)
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
             a[r] = *reinterpret_cast<const float4*>(&Rs[(ty * RPT + r) * r_ld + i0 + ii]);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            b[q] = *reinterpret_cast<const float4*>(&Ws[(ii + q) * (kBlk + kPad) + tx * 4]);
+            b[q] = *reinterpret_cast<const float4*>(&Ws[(ii + q) * (BLK + kPad) + tx * 4]);
 #pragma unroll
           for (int r = 0; r < RPT; ++r) {
             acc[r][0] = fmaf(a[r].x, b[0].x, acc[r][0]);
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, TM == 64 ? 2 : 3) fista_ffma_kernel(
   __syncthreads();
   if (tid == 0) {
     double sa = 0.0, sb = 0.0, sc = 0.0, sd = 0.0;
-    for (int wi = 0; wi < kThreads / 32; ++wi) {
+    for (int wi = 0; wi < NT / 32; ++wi) {
       sa += red[wi][0];
       sb += red[wi][1];
       sc += red[wi][2];
@@ -364,9 +369,9 @@ __global__ void momentum_kernel(const float* __restrict__ z_next, const float* _
   }
 }
 
-size_t smem_bytes(int tm, int d) {
+size_t smem_bytes(int tm, int d, int blk = kBlk) {
   const int d_pad = (d + 3) & ~3;
-  size_t ws = (size_t)max(kBlk * (kCk + kPad), kCk * (kBlk + kPad));
+  size_t ws = (size_t)max(blk * (kCk + kPad), kCk * (blk + kPad));
   return sizeof(float) * ((size_t)tm * (d_pad + kPad) + (size_t)tm * (kCk + kPad) + ws);
 }
 
@@ -384,41 +389,57 @@ int pick_tm(int d) {
   return 0;
 }
 
-template <int TM, int MODE>
-int launch(const StepParams& p, cudaStream_t st) {
+int sm_count() {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
-    LASSO_CUDA_TRY(cudaGetDevice(&dev));
-    LASSO_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms < 1)
+      num_sms = 148;
   }
-  const size_t smem = smem_bytes(TM, p.d);
+  return num_sms;
+}
+
+template <int TM, int MODE, int BLK>
+int launch(const StepParams& p, cudaStream_t st) {
+  const int num_sms = sm_count();
+  const size_t smem = smem_bytes(TM, p.d, BLK);
   static size_t configured = 0;
   if (smem > configured) {
-    LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_ffma_kernel<TM, MODE>,
+    LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_ffma_kernel<TM, MODE, BLK>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   int per_sm = 1;
   LASSO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, fista_ffma_kernel<TM, MODE>, kThreads, smem));
+      &per_sm, fista_ffma_kernel<TM, MODE, BLK>, BLK * 4, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t ntiles = (p.n + TM - 1) / TM;
   int64_t grid = (int64_t)num_sms * per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  fista_ffma_kernel<TM, MODE><<<(unsigned)grid, kThreads, smem, st>>>(p);
+  fista_ffma_kernel<TM, MODE, BLK><<<(unsigned)grid, BLK * 4, smem, st>>>(p);
   LASSO_CHECK_LAUNCH();
   count_launch();
   return LASSO_B200_OK;
 }
 
+// Wide blocks (128 columns, 512 threads): tuning variant, LASSO_B200_FFMA_BLK=128.  Measured no better than
+// 64-column blocks: 21.97 vs 20.11 ms per 20 iterations at n=65536, d=289, k=300, and within the run-to-run
+// spread (115-132 EM steps/s) on the notebook configuration (n=10000), so it is never picked automatically.
+bool use_wide_blocks(const StepParams& p) {
+  if (smem_bytes(64, p.d, 128) > 200 * 1024) return false;
+  const char* e = getenv("LASSO_B200_FFMA_BLK");
+  return e != nullptr && atoi(e) == 128;
+}
+
 template <int MODE>
 int dispatch(const StepParams& p, cudaStream_t st) {
+  if (pick_tm(p.d) == 64 && use_wide_blocks(p)) return launch<64, MODE, 128>(p, st);
   switch (pick_tm(p.d)) {
-    case 64: return launch<64, MODE>(p, st);
-    case 32: return launch<32, MODE>(p, st);
-    case 16: return launch<16, MODE>(p, st);
+    case 64: return launch<64, MODE, kBlk>(p, st);
+    case 32: return launch<32, MODE, kBlk>(p, st);
+    case 16: return launch<16, MODE, kBlk>(p, st);
     default:
       set_error("FFMA path: d=%d needs more shared memory than one SM has", p.d);
       return LASSO_B200_ERR_UNSUPPORTED;

@@ -204,6 +204,31 @@ def test_blocked_kernel_warm_start_stop_test_and_fallback(dev, monkeypatch):
     assert torch.equal(got, ffma)
 
 
+def test_ffma_wide_blocks_bit_identical(dev, monkeypatch):
+    # the FFMA kernel's 128-column-block / 512-thread variant (LASSO_B200_FFMA_BLK=128, a tuning knob): the
+    # contraction order per output is unchanged, so the codes, the loss terms and the line-search building
+    # blocks must equal the 64-column kernel's bit for bit -- and match the oracle
+    n, d, k, iters = 700, 200, 300, 30
+    x, w = make_problem(n, d, k, seed=3)
+    xd, wd = x.to(dev), w.to(dev)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    z0 = (0.05 * torch.randn(n, k)).to(dev)
+    out = {}
+    for blk in ("64", "128"):
+        monkeypatch.setenv("LASSO_B200_FFMA_BLK", blk)
+        z, _, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, iters, True, -1.0, path="ffma")
+        grad, f_sum = _cabi.gradient(xd, z, wd)
+        out[blk] = (z, grad, f_sum.clone(), lasso_loss(xd, z, wd, 0.1))
+    monkeypatch.delenv("LASSO_B200_FFMA_BLK")
+    assert torch.equal(out["64"][0], out["128"][0]) and torch.equal(out["64"][1], out["128"][1])
+    assert abs(float(out["64"][2]) - float(out["128"][2])) <= 1e-9 * abs(float(out["64"][2]))
+    assert abs(float(out["64"][3]) - float(out["128"][3])) <= 1e-6 * abs(float(out["64"][3]))
+    auto, _, _ = _cabi.fista_device(xd, wd, z0, 0.1, lr, iters, True, -1.0, path="ffma")
+    assert torch.equal(auto, out["128"][0])
+    want = oracle.ista(x, z0.cpu(), w, alpha=0.1, lr=lr, maxiter=iters, tol=0.0)
+    assert rel_fro(auto, want) <= TOL
+
+
 def test_resident_rows_at_wildly_different_scales(dev):
     # every row is its own lasso problem and is rescaled on its own: the relative error of EACH
     # row stays at the float32 level although the batch spans 12 orders of magnitude
