@@ -145,3 +145,81 @@ def test_sharded_stop_rule_two_ranks(tmp_path, tol, maxiter):
         assert want_done < maxiter
     # rows are independent: the sharded run equals the unsharded one bit for bit
     assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------
+# 2-rank gloo: the M-step all-reduces the packed statistics [Z^T Z | Z^T X] (and the two loss sums)
+# once, then every rank runs the same atom sweep: dictionaries identical on all ranks and equal to the
+# unsharded update
+# ---------------------------------------------------------------------------------------
+
+class _FakeCuda(torch.Tensor):
+    """A CPU tensor that answers is_cuda = True (host logic only; the CUDA calls are stubbed)."""
+    @property
+    def is_cuda(self):
+        return True
+
+
+def _stub_gram(z, x):
+    z64, x64 = torch.Tensor(z).double(), torch.Tensor(x).double()
+    return z64.T @ z64, z64.T @ x64
+
+
+def _stub_dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None, positive=False):
+    new, zeroed = oracle.update_dict_gram(torch.Tensor(dictionary), gzz, gzx, eps=eps, positive=positive)
+    keep = [j for j in range(new.size(1)) if j not in zeroed]
+    torch.Tensor(dictionary)[:, keep] = new[:, keep]
+    mask = torch.zeros(new.size(1), dtype=torch.int32)
+    mask[zeroed] = 1
+    return mask
+
+
+def _stub_loss_terms(x, z, w):
+    x, z, w = torch.Tensor(x).double(), torch.Tensor(z).double(), torch.Tensor(w).double()
+    return torch.stack([(z @ w.T - x).square().sum(), z.abs().sum()])
+
+
+def _mstep_problem():
+    x, w = make_problem(96, 12, 24, seed=31, kind="planted")
+    z = oracle.ista(x, torch.zeros(96, 24), w, alpha=0.05, lr=1.0 / oracle.lipschitz_constant(w), maxiter=40, tol=0.0)
+    z[:, 5] = 0                       # an unused atom: flagged on every rank, re-drawn identically (broadcast)
+    return x, w, z
+
+
+def _mstep_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import lasso_b200 as pkg
+        from lasso_b200.linear import lasso_loss, update_dict, update_dict_ridge
+        pkg._cabi.gram = _stub_gram
+        pkg._cabi.dict_update_gram = _stub_dict_update_gram
+        pkg._cabi.loss_terms = _stub_loss_terms
+        x, w, z = _mstep_problem()
+        rows = slice(0, 40) if rank == 0 else slice(40, 96)          # ragged shards
+        xs, zs = x[rows].clone(), z[rows].clone()
+        torch.manual_seed(100 + rank)                                 # ranks draw differently: rank 0's draw wins
+        d_new = update_dict(w.clone().as_subclass(_FakeCuda), xs, zs, group=dist.group.WORLD)
+        v_new = update_dict_ridge(xs, zs, lambd=1e-2, group=dist.group.WORLD)
+        loss = lasso_loss(xs, zs, w, 0.05, group=dist.group.WORLD)
+        torch.save({"d": torch.Tensor(d_new).clone(), "v": v_new, "loss": float(loss), "z5": float(zs[:, 5].abs().max())},
+                   os.path.join(result_dir, "m%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_mstep_two_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_mstep_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    x, w, z = _mstep_problem()
+    parts = [torch.load(os.path.join(str(tmp_path), "m%d.pt" % r)) for r in range(2)]
+    # replicated dictionary without a broadcast of the result: identical bits on both ranks
+    assert torch.equal(parts[0]["d"], parts[1]["d"]) and torch.equal(parts[0]["v"], parts[1]["v"])
+    assert parts[0]["loss"] == parts[1]["loss"]
+    want = oracle.update_dict(w.clone(), x, z.clone())
+    keep = [j for j in range(24) if j != 5]
+    assert rel_fro(parts[0]["d"][:, keep], want[:, keep]) <= 1e-5
+    assert abs(float(parts[0]["d"][:, 5].norm()) - 1.0) <= 1e-6 and parts[0]["z5"] == 0.0
+    assert rel_fro(parts[0]["v"], oracle.update_dict_ridge(x, z, lambd=1e-2)) <= 1e-5
+    assert abs(parts[0]["loss"] - float(oracle.lasso_loss(x, z, w, 0.05))) <= 1e-6 * abs(parts[0]["loss"])
