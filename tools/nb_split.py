@@ -1,5 +1,5 @@
 import os, sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, lasso_b200
 from lasso_b200 import _cabi
 from lasso_b200.linear import sparse_encode, lasso_loss, update_dict, update_dict_ridge, initialize_code
