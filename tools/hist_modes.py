@@ -1,5 +1,6 @@
+import os
 import sys, os, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, lasso_b200, oracle
 from lasso_b200 import _cabi
 from lasso_b200.testing import make_problem
