@@ -45,7 +45,8 @@ constexpr int kKP = 256;           // padded k
 constexpr int kThreadsR = 544;     // warps 0..15: compute, warp 16: MMA issuer (the SM's warp arbiter favours
                                    // high warp ids: as warp 0 the issuer starved behind the epilogue math)
 // (registers: the SM hands them out per 4 warps, so 17 warps are budgeted as 20 and 96 per thread is
-// the ceiling -- a 112-register build fails to launch)
+// the ceiling -- a 112-register build fails to launch; setmaxnreg would let the compute warps grow, but
+// ptxas 12.9 refuses to allocate this kernel once the instruction is present)
 constexpr uint32_t kSlabBytes = kDP * 128;                 // [64 features][128 B] = 64 atoms of one piece
 constexpr uint32_t kPieceBytes = (kKP / 64) * kSlabBytes;  // 32 KB
 constexpr uint32_t kWBytes = 2 * kPieceBytes;              // 64 KB: h image, l image
@@ -54,11 +55,11 @@ constexpr uint32_t kSmemZ = kSmemW + kWBytes;              // [128][256] fp32, 1
 constexpr uint32_t kSmemX = kSmemZ + kTileM * kKP * 4;     // [128][64] fp32, 256 B rows
 constexpr uint32_t kSmemBytesR = kSmemX + kTileM * kDP * 4;   // 229376
 
-constexpr uint32_t kColY = 0;         // y, fp32
-constexpr uint32_t kColStage = 256;   // piece slot S: [h 32 cols][l 32 cols] = 64 atoms of y
-constexpr uint32_t kColR = 320;       // r pieces: [h 32 cols][l 32 cols] = 64 features
-constexpr uint32_t kColAccR = 384;    // R = Y W^T (GEMM1)
-constexpr uint32_t kColAccG = 448;    // G = r W, one 64-atom chunk (GEMM2)
+constexpr uint32_t kColY = 0;         // y chunks 0..2, fp32 (chunk 3: registers)
+constexpr uint32_t kColS = 192;       // piece slot S: [h 32 cols][l 32 cols] = 64 atoms of y (even chunks)
+constexpr uint32_t kColQ = 256;       // r pieces [h 32][l 32] = 64 features during GEMM2, then the slot of the odd chunks
+constexpr uint32_t kColAccR = 320;    // R = Y W^T (GEMM1)
+constexpr uint32_t kColAccG = 384;    // G = r W, two buffers of one 64-atom chunk (GEMM2)
 constexpr uint32_t kTmemCols = 512;
 
 constexpr float kPieceLimit = 32768.0f;   // |operand| beyond this: fall back (fp16 max 65504)
@@ -83,40 +84,52 @@ struct ResParams {
   bool vec_x, vec_z0, vec_z; // rows of x / z0 / z_out are 16-byte aligned (float4 access)
 };
 
-__device__ __noinline__ void res_wait_slow_path(uint64_t& t0, volatile int* dbg, int line, uint32_t parity) {
-  const uint64_t now = global_timer_ns();
-  if (t0 == 0) {
-    t0 = now;
-    return;
-  }
-  if (now - t0 < 4000000000ull) return;
-  if (dbg) {
-    dbg[1] = line; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x; dbg[4] = -1; dbg[5] = (int)parity;
-    __threadfence_system();
-    dbg[0] = 1;
-    __threadfence_system();
-  }
-  __trap();
-}
 #ifndef LASSO_RES_HINT
 #define LASSO_RES_HINT 20000   // suspend-time hint of the waits, ns (0 / 1000 / 20000 measure the same)
 #endif
+// Slow path of a barrier wait, out of line: the first test failed.  A protocol bug must not hang
+// the GPU: after 4 s the wait records where it stood (LASSO_B200_DEBUG) and traps.
+__device__ __noinline__ void res_wait_spin(uint32_t addr, uint32_t par, volatile int* dbg, int line) {
+  uint64_t t0 = 0;
+  uint32_t n = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(par), "r"((unsigned)LASSO_RES_HINT)
+        : "memory");
+    if (ok) return;
+    if ((++n & 255u) != 0) continue;
+    const uint64_t now = global_timer_ns();
+    if (t0 == 0) {
+      t0 = now;
+      continue;
+    }
+    if (now - t0 < 4000000000ull) continue;
+    if (dbg) {
+      dbg[1] = line; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x; dbg[4] = -1; dbg[5] = (int)par;
+      __threadfence_system();
+      dbg[0] = 1;
+      __threadfence_system();
+    }
+    __trap();
+  }
+}
 #define RES_WAIT(bar, parity)                                                             \
   do {                                                                                    \
     const uint32_t _addr = smem_u32(bar), _par = (parity) & 1u;                           \
-    uint32_t _ok, _n = 0;                                                                 \
-    uint64_t _t0 = 0;                                                                     \
-    for (;;) {                                                                            \
-      asm volatile(                                                                       \
-          "{\n\t.reg .pred P;\n\t"                                                       \
-          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"                  \
-          "selp.b32 %0, 1, 0, P;\n\t}\n"                                                   \
-          : "=r"(_ok)                                                                     \
-          : "r"(_addr), "r"(_par), "r"((unsigned)LASSO_RES_HINT)                          \
-          : "memory");                                                                    \
-      if (_ok) break;                                                                     \
-      if ((++_n & 1023u) == 0) res_wait_slow_path(_t0, p.dbg, __LINE__, _par);            \
-    }                                                                                     \
+    uint32_t _ok;                                                                         \
+    asm volatile(                                                                         \
+        "{\n\t.reg .pred P;\n\t"                                                         \
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"                        \
+        "selp.b32 %0, 1, 0, P;\n\t}\n"                                                     \
+        : "=r"(_ok)                                                                       \
+        : "r"(_addr), "r"(_par)                                                           \
+        : "memory");                                                                      \
+    if (!_ok) res_wait_spin(_addr, _par, p.dbg, __LINE__);                                \
   } while (0)
 
 // timeline instrumentation (block 0, lane 0 of every warp, iterations 3 and 4 of its first
@@ -240,21 +253,32 @@ __device__ __noinline__ bool res_store_tile(const ResParams& p, const uint8_t* z
 // Schedule of one iteration (NQ = 4 chunks of 64 atoms; all 16 compute warps work on the same
 // chunk, each thread on 16 atoms of one row):
 //
-//   MMA warp   GEMM2 q0 | q1 | G1' q0 | GEMM2 q2 | G1' q1 | GEMM2 q3 | G1' q2 | G1' q3 ... (B) GEMM2 q0
-//   compute          C(0)     |    C(1)     |    C(2)     |    C(3)     | idle |   B   | idle
+//   MMA warp   GEMM2 q0 | q1 | q2 | q3 | G1' q0 | G1' q1 | G1' q2 | G1' q3 ........ (B) GEMM2 q0 | q1
+//   compute        C(0)      |    C(1)     |    C(2)     |    C(3)     | idle |  B  | idle
 //
 // C(q): z+ = softshrink(y - lr g, lam), stop-test record, y+ = z+ + beta (z+ - z) in place, then
-// the fp16 pieces of y+ go to the piece slot S, where the slice q of the NEXT iteration's GEMM1
-// (G1') picks them up.  GEMM1 has its own accumulator R, so it trails the epilogue by one chunk
-// instead of waiting for it to finish; the G accumulator and the slot are single-buffered, which
-// costs nothing because a chunk's epilogue (~1000 cycles) outlasts its MMAs (~500).
-// TMEM columns: y 256 | S 64 | r pieces 64 | R 64 | G 64 = 512.
+// the fp16 pieces of y+ go to a piece slot, where slice q of the NEXT iteration's GEMM1 (G1')
+// picks them up.  The tensor pipe is the busier side (96 MMAs ~ 4.1 k cycles per iteration against
+// ~3.4 k issue cycles of epilogue), so the MMA queue must never wait on the epilogue:
+//   * G has two buffers: GEMM2 q+1 runs while C(q) drains buffer q & 1, GEMM2 q+2 starts as soon as
+//     C(q) has the accumulator in registers;
+//   * the pieces have two slots: even chunks go to S, odd chunks to Q -- the columns that hold the
+//     pieces of r during GEMM2 and are dead once GEMM2 q3 has completed;
+//   * the 64 columns this needs come from y: chunk 3 of y lives in registers (16 per thread).
+// TMEM columns: y chunks 0-2 192 | S 64 | Q (r pieces / odd slots) 64 | R 64 | G0 64 | G1 64 = 512.
+// Barriers (each completes once per iteration of a tile; phase = global iteration counter):
+//   aready[q]  512 arrivals   pieces of chunk q stored             compute -> MMA
+//   sfree[j]   commit         G1' slice j done: slot j & 1 is free for chunk j + 2   MMA -> compute
+//   rfull      commit         GEMM1 complete                       MMA -> compute
+//   rready     512 arrivals   pieces of r stored                   compute -> MMA
+//   gfull[q]   commit         GEMM2 chunk q complete               MMA -> compute
+//   gfree[j]   512 arrivals   C(j) has G buffer j in registers     compute -> MMA (GEMM2 j + 2)
 // kHist: 0 no stop-test record, 1 hist[it] += sum |z+ - z| (ista.py:93), 2 hist[it] += 1 if any
 // z+ != z (all a threshold of exactly 0 needs; cheaper than the sum)
 template <int NQ, int kHist>
 __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_w, bar_aready, bar_sfree, bar_rfull, bar_rready, bar_gfull, bar_gfree;
+  __shared__ uint64_t bar_w, bar_rfull, bar_rready, bar_aready[4], bar_sfree[2], bar_gfull[4], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float row_sx[kTileM];   // per-row power-of-two scale of x (see the file header)
   __shared__ float hist_s[2][16];    // per-warp stop-test records of the last two iterations
@@ -265,12 +289,18 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_aready, 512);
-    mbar_init(&bar_sfree, 1);
-    mbar_init(&bar_gfull, 1);
-    mbar_init(&bar_gfree, 512);
     mbar_init(&bar_rfull, 1);
     mbar_init(&bar_rready, 512);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mbar_init(&bar_aready[q], 512);
+      mbar_init(&bar_gfull[q], 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&bar_sfree[j], 1);
+      mbar_init(&bar_gfree[j], 512);
+    }
     fence_mbar_init();
   }
   if (warp == 16) {
@@ -302,14 +332,14 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     auto make64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
     int tr_n = 0;
     bool tr_on = false;
-    // slice q of GEMM1 of iteration `tg`: R (+)= Y[:, 64 q ...] W^T, three products per k-step
+    // slice q of GEMM1 of pass `tg`: R (+)= Y[:, 64 q ...] W^T, three products per k-step
     // into ONE accumulator (small ones first)
     auto gemm1_slice = [&](int q, uint32_t tg) {
-      RES_WAIT(&bar_aready, tg * (uint32_t)NQ + (uint32_t)q);
+      RES_WAIT(&bar_aready[q], tg);
       RTRACE(11);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t t_slot = tbase + kColStage;
+        const uint32_t t_slot = tbase + ((q & 1) ? kColQ : kColS);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t koff = (uint32_t)q * (kSlabBytes >> 4) + (uint32_t)(ks * 2);
@@ -320,8 +350,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           mma_ts<false>(tbase + kColAccR, al, qh, idesc1, 1);
           mma_ts<false>(tbase + kColAccR, ah, qh, idesc1, 1);
         }
+        if (q + 2 < NQ) mma_commit(&bar_sfree[q]);   // the slot may take the pieces of chunk q + 2
         if (q == NQ - 1) mma_commit(&bar_rfull);
-        else mma_commit(&bar_sfree);
       }
       __syncwarp();
       RTRACE(12);
@@ -341,47 +371,65 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         tc_fence_after();
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          // ---- GEMM2 chunk q: G = r W[:, 64 q ...]; the single G buffer must have been drained ----
-          if (q >= 1) RES_WAIT(&bar_gfree, gi * (uint32_t)NQ + (uint32_t)q - 1u);
+          // ---- GEMM2 chunk q: G[q & 1] = r W[:, 64 q ...]; chunk q - 2 must have left the buffer ----
+          if (q >= 2) {
+            RES_WAIT(&bar_gfree[q - 2], gi);
+            tc_fence_after();
+          }
           RTRACE(15);
-          tc_fence_after();
           if (elect_one()) {
-            const uint32_t t_acc = tbase + kColAccG;
-            const uint32_t t_r = tbase + kColR;
+            const uint32_t t_acc = tbase + kColAccG + (uint32_t)(q & 1) * 64u;
+            const uint32_t t_r = tbase + kColQ;
             const uint32_t qoff = (uint32_t)q * (kSlabBytes >> 4);
-            uint32_t acc_on = 0;
             // small products first (l h', h l'), leading product last
+            constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+            if (dsteps == 4) {
+              // d > 48: straight-line issue (the predicated form below costs the issuing thread ~15 cycles
+              // more per MMA, which the tensor pipe then waits for)
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+              for (int t = 0; t < 3; ++t) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks < dsteps) {
+                for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
-                  mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
-                  acc_on = 1;
+                  mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, (t > 0 || ks > 0) ? 1u : 0u);
+                }
+              }
+            } else {
+              uint32_t acc_on = 0;
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                  if (ks < dsteps) {
+                    const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
+                    mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
+                    acc_on = 1;
+                  }
                 }
               }
             }
-            mma_commit(&bar_gfull);
+            mma_commit(&bar_gfull[q]);
           }
           __syncwarp();
           RTRACE(16);
-          if (kHist != 0 && q == 0 && it > 0 && lane == 0) {
-            // stop-test record of the previous iteration: the compute warps left their partial
-            // sums in shared memory before they arrived on bar_rready; ONE atomic per CTA
-            double s = 0.0;
-#pragma unroll
-            for (int wi = 0; wi < 16; ++wi) s += (double)hist_s[(it - 1) & 1][wi];
-            if (kHist == 1 || s > 0.0) atomicAdd(p.hist + it - 1, s);
-          }
-          // ---- GEMM1 of the next iteration trails the epilogue by one chunk ----
-          if (more && q >= 1) gemm1_slice(q - 1, gi + 1);
         }
-        if (more) gemm1_slice(NQ - 1, gi + 1);
+        if (kHist == 1 && it > 0 && lane == 0) {
+          // stop-test record of the previous iteration: the compute warps left their partial
+          // sums in shared memory before they arrived on bar_rready; ONE atomic per CTA, issued
+          // while the tensor pipe works through the four GEMM2 chunks just queued
+          double s = 0.0;
+#pragma unroll
+          for (int wi = 0; wi < 16; ++wi) s += (double)hist_s[(it - 1) & 1][wi];
+          atomicAdd(p.hist + it - 1, s);
+        }
+        // ---- GEMM1 of the next iteration, slice by slice as the epilogue delivers the pieces ----
+        if (more) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) gemm1_slice(q, gi + 1);
+        }
       }
     }
-  } else {
+  } else if (warp < 16) {
     // ===================== compute warps =====================
     const int quad = warp & 3;                 // TMEM lane quadrant of this warp
     const int wg = warp >> 2;                  // group 0..3: atoms [16 wg, 16 wg + 16) of every chunk,
@@ -397,26 +445,32 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     bool tr_on = false;
     bool bad = false;
     uint32_t gi = 0;
+    uint32_t yk[16];                           // chunk 3 of y (NQ = 4): registers, not TMEM
+#pragma unroll
+    for (int j = 0; j < 16; ++j) yk[j] = 0u;
 
-    // 16 values -> fp16 pieces -> this thread's 8 + 8 words of the slot [h 32 cols][l 32 cols];
-    // chunk q of the GEMM1 of iteration `tg`
-    auto stage_pieces = [&](const uint32_t (&yv)[16], int q, uint32_t tg) {
+    // 16 values -> fp16 pieces -> this thread's 8 + 8 words of a slot [h 32 cols][l 32 cols]
+    // (even chunks: S, odd chunks: Q); chunk q of the GEMM1 of pass `tg`.  first = the tile's
+    // first pass (pieces of y_0): Q is not in use by a GEMM2 then.
+    auto stage_pieces = [&](const uint32_t (&yv)[16], int q, uint32_t tg, bool first) {
       uint32_t wh[8], wl[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         split2_pair(make_float2(__uint_as_float(yv[2 * j]), __uint_as_float(yv[2 * j + 1])), wh[j], wl[j]);
       RTRACE(21);
-      // the slot is free once slice q - 1 has been consumed (q = 0: GEMM1 of the previous
-      // iteration is complete, everybody saw bar_rfull)
-      if (q >= 1) RES_WAIT(&bar_sfree, tg * (uint32_t)(NQ - 1) + (uint32_t)q - 1u);
+      // chunk 0 -> S: free since GEMM1 of the previous pass completed (everybody saw bar_rfull);
+      // chunk 1 -> Q: the last GEMM2 chunk of this iteration must have read the pieces of r;
+      // chunks 2, 3: slice q - 2 of this pass must have consumed the slot
+      if (q == 1 && !first) RES_WAIT(&bar_gfull[NQ - 1], tg - 1u);
+      if (q >= 2) RES_WAIT(&bar_sfree[q - 2], tg);
       RTRACE(22);
-      const uint32_t t_slot = tbase + lane_base + kColStage + wg * 8;
+      const uint32_t t_slot = tbase + lane_base + ((q & 1) ? kColQ : kColS) + wg * 8;
       tc_fence_after();
       tmem_st8(t_slot, wh);
       tmem_st8(t_slot + 32, wl);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bar_aready);
+      mbar_arrive(&bar_aready[q]);
       RTRACE(23);
     };
 
@@ -440,8 +494,13 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           yv[4 * j + 2] = __float_as_uint(z4.z);
           yv[4 * j + 3] = __float_as_uint(z4.w);
         }
-        tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
-        stage_pieces(yv, q, gi);
+        if (q < 3) {
+          tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yk[j] = yv[j];
+        }
+        stage_pieces(yv, q, gi, true);
       }
 
       float beta_next = __ldg(p.beta);         // fetched one iteration ahead: a global load costs ~600 cycles
@@ -450,7 +509,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         const bool more = it + 1 < iters;      // pieces are only needed if another GEMM1 follows
         const float2 beta2 = make_float2(beta_next, beta_next);
         if (more) beta_next = __ldg(p.beta + it + 1);
-        // ---------------- phase B: r = R - x -> pieces (16 features per thread) ----------------
+        // ---------------- phase B: r = R - x -> pieces (16 features per thread) -> Q ----------------
         {
           float4 xv[4];
 #pragma unroll
@@ -471,7 +530,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
             split2_pair(ra, wh[2 * j], wl[2 * j]);
             split2_pair(rc, wh[2 * j + 1], wl[2 * j + 1]);
           }
-          const uint32_t t_r = tbase + lane_base + kColR + wg * 8;
+          const uint32_t t_r = tbase + lane_base + kColQ + wg * 8;
           tmem_st8(t_r, wh);
           tmem_st8(t_r + 32, wl);
           tmem_wait_st();
@@ -486,20 +545,26 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         for (int q = 0; q < NQ; ++q) {
           // y does not depend on the MMAs: its load is in flight while this thread waits for G
           uint32_t g[16], yv[16];
-          tmem_ld16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
-          RES_WAIT(&bar_gfull, gi * (uint32_t)NQ + (uint32_t)q);
+          if (q < 3) {
+            tmem_ld16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) yv[j] = yk[j];
+          }
+          RES_WAIT(&bar_gfull[q], gi);
           RTRACE(40);
           tc_fence_after();
-          tmem_ld16(tbase + lane_base + kColAccG + wg * 16, g);
+          tmem_ld16(tbase + lane_base + kColAccG + (q & 1) * 64 + wg * 16, g);
           tmem_wait_ld();
-          tc_fence_before();
-          mbar_arrive(&bar_gfree);   // accumulator is in registers: hand the buffer back
+          if (q + 2 < NQ) {
+            tc_fence_before();
+            mbar_arrive(&bar_gfree[q]);   // accumulator is in registers: hand the buffer to chunk q + 2
+          }
           RTRACE(42);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint8_t* zp = zs + z_off(row, q * 16 + wg * 4 + j);
-            const float4 z4 = *reinterpret_cast<const float4*>(zp);
-            float2 zo[2];
+            float4 z4 = *reinterpret_cast<const float4*>(zp);
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const float2 yy = make_float2(__uint_as_float(yv[4 * j + 2 * h2]), __uint_as_float(yv[4 * j + 2 * h2 + 1]));
@@ -517,16 +582,22 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
               }
               if (kHist == 2) any |= __float_as_uint(dl.x) | __float_as_uint(dl.y);
               const float2 yn = __ffma2_rn(beta2, dl, zn);           // ista.py:100
-              zo[h2] = zn;
+              if (h2) { z4.z = zn.x; z4.w = zn.y; }
+              else { z4.x = zn.x; z4.y = zn.y; }
               yv[4 * j + 2 * h2] = __float_as_uint(yn.x);
               yv[4 * j + 2 * h2 + 1] = __float_as_uint(yn.y);
             }
-            *reinterpret_cast<float4*>(zp) = make_float4(zo[0].x, zo[0].y, zo[1].x, zo[1].y);
+            *reinterpret_cast<float4*>(zp) = z4;
           }
-          tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
+          if (q < 3) {
+            tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) yk[j] = yv[j];
+          }
           RTRACE(41);
-          if (more) stage_pieces(yv, q, gi + 1);   // its wait::st also covers the y store
-          else tmem_wait_st();
+          if (more) stage_pieces(yv, q, gi + 1, false);   // its wait::st also covers the y store
+          else if (q < 3) tmem_wait_st();
         }
         if (kHist != 0) {
           float s;
@@ -538,10 +609,16 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
             s = __any_sync(0xffffffffu, (any & 0x7FFFFFFFu) != 0u) ? 1.f : 0.f;
           }
           if (lane == 0) {
-            // the MMA warp adds the 16 partial records up after the next bar_rready (one atomic
-            // per CTA and iteration); nobody comes after a tile's last iteration
-            if (more) hist_s[it & 1][warp] = s;
-            else if (kHist == 1 || s > 0.f) atomicAdd(p.hist + it, (double)s);
+            if (kHist == 2) {
+              // "something moved" needs no sum: a plain store of the same value from whoever saw it
+              if (s > 0.f) p.hist[it] = 1.0;
+            } else if (more) {
+              // the MMA warp adds the 16 partial records up after the next bar_rready (one atomic
+              // per CTA and iteration); nobody comes after a tile's last iteration
+              hist_s[it & 1][warp] = s;
+            } else {
+              atomicAdd(p.hist + it, (double)s);
+            }
           }
         }
         ++gi;
