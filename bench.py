@@ -16,8 +16,16 @@ lr pinned, tol=0 -- BASELINE.md section 4).  Prints ONE JSON line (rank 0).
             flops 4*n*d*k*iterations per launch / launch duration vs the measured dense bf16
             rate.  Streaming kernels (--path tcgen05 | ffma, one launch per iteration): HBM bound,
             algorithmic bytes n*(d+3k)*4 per launch vs the measured copy bandwidth.
-  cpu_baseline / --impl reference: the oracle port of the reference's PyTorch CPU loop
-            on the host cores (the reference itself cannot travel to the GPU box)
+  cpu_baseline / --impl reference: the reference's own PyTorch CPU loop (lasso.linear.solvers.ista,
+            the unmodified package copied to oracle/_ref by oracle/Makefile; kind "reference") on the
+            host cores, same 200 iterations per step; the oracle port (kind "port") only if that copy
+            is absent
+  strong    the ONE 65536-row batch row-sharded over the N ranks through sparse_encode(group=...)
+            (deferred, all-reduced stop test): iterations/s at fixed total work
+  dict_learning_c4   BASELINE config 4: ms per EM step at 131072 rows per rank (100 FISTA iterations,
+            Gram statistics, ONE all-reduce, replicated atom sweep), the all-reduce timed by itself
+  gpu_eager_baseline  the reference's loop as stock torch ops on the same B200 (N = 1 only)
+  e2e_roofline        pinned H2D / D2H bandwidth per rank and the time the step's copies need alone
 """
 from __future__ import annotations
 
@@ -123,52 +131,74 @@ class ClockSampler:
                 "samples": len(inside), "window": window, "reasons": reasons}
 
 
-def cpu_reference_rate(x, w, lr, budget_s=12.0, threads=None):
-    """Oracle port of the reference's CPU loop, timed on a bounded sample."""
-    import torch
+def reference_ista():
+    """(callable, kind): the reference's own ista from oracle/_ref, else the oracle port."""
     import oracle
+    from oracle import ref_loader
+    fn = ref_loader.ista()
+    if fn is not None:
+        return fn, "reference"
+    return oracle.ista, "port"
+
+
+def cpu_reference_rate(x, w, lr, budget_s=12.0, threads=None):
+    """The reference's CPU loop (oracle/_ref, else the oracle port), timed on a bounded sample."""
+    import torch
+    fn, kind = reference_ista()
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     z0 = torch.zeros(x.size(0), w.size(1))
-    oracle.ista(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=2, tol=0.0)       # warm-up
+    fn(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=2, tol=0.0)       # warm-up
     t0 = time.perf_counter()
-    oracle.ista(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=4, tol=0.0)
+    fn(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=4, tol=0.0)
     per_it = (time.perf_counter() - t0) / 4
     iters = int(max(8, min(400, budget_s / max(per_it, 1e-6))))
     t0 = time.perf_counter()
-    oracle.ista(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=iters, tol=0.0)
+    fn(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=iters, tol=0.0)
     dt = time.perf_counter() - t0
-    return iters / dt, iters, torch.get_num_threads()
+    return iters / dt, iters, torch.get_num_threads(), kind
 
 
 def run_reference(args, rank, world):
+    """The reference arm: lasso.linear.solvers.ista.ista (unmodified, from oracle/_ref) on the host
+    cores, the same configuration as our arm: 200 FISTA iterations per step on the 65536 x 64 batch."""
     if rank != 0:
         return
-    import torch  # noqa: F401
-    import oracle
-    x, w, lr = problem()
-    threads = os.cpu_count() or 1
     import torch
+    x, w, lr = problem()
+    fn, kind = reference_ista()
+    threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     z0 = torch.zeros(N_ROWS, K)
-    sample_iters = 5   # per step: bounded sample of the 200-iteration solve (constant cost/iter)
-    for _ in range(max(args.warmup, 1)):
-        oracle.ista(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=sample_iters, tol=0.0)
+    # one warm-up step is enough for a CPU loop (thread pool, allocator); more would only cost minutes
+    warm = 1 if args.warmup > 0 else 0
+    for _ in range(warm):
+        fn(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=MAXITER, tol=0.0)
+    # bounded: stop after the requested steps or ~4 minutes, whichever comes first (>= 2 steps)
     t0 = time.perf_counter()
+    done = 0
     for _ in range(args.steps):
-        oracle.ista(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=sample_iters, tol=0.0)
+        fn(x, z0, w, alpha=ALPHA, fast=True, lr=lr, maxiter=MAXITER, tol=0.0)
+        done += 1
+        if done >= 2 and time.perf_counter() - t0 > 240.0:
+            break
     dt = time.perf_counter() - t0
-    value = args.steps * sample_iters / dt
-    sample = "{} FISTA iterations per step on the full 65536x64 batch (cost per iteration is constant)".format(sample_iters)
+    value = done * MAXITER / dt
+    sample = ("{} steps of {} FISTA iterations on the full 65536x64 batch ({} warm-up step)"
+              .format(done, MAXITER, warm))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": done, "warmup": warm, "ms_per_step": 1e3 * dt / done,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: FISTA n=65536 d=64 k=256 alpha=0.1 fp32, tol=0, lr pinned",
-                   "iters_per_step": sample_iters, "device": "host CPU (torch {})".format(torch.__version__)},
+        "config": {"workload": "configs[1]: FISTA n=65536 d=64 k=256 alpha=0.1 fp32, 200 iterations per "
+                               "step, tol=0, lr pinned, planted-sparse X (seed 0)",
+                   "iters_per_step": MAXITER,
+                   "implementation": "lasso.linear.solvers.ista.ista (oracle/_ref, unmodified)" if kind == "reference"
+                   else "oracle.ista (port; oracle/_ref absent)",
+                   "device": "host CPU (torch {})".format(torch.__version__)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(),
-                         "kind": "port", "sample": sample},
+                         "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -251,12 +281,158 @@ def run_ours(args, rank, local_rank, world):
     e2e_steps = max(2, min(args.steps, 5))
     ms_e2e = timed(e2e_step, e2e_steps)
 
+    def reduce_scalar(v, op):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # ---- e2e roofline: what the PCIe / host-memory side of one step can do, per rank ----
+    # (all ranks copy at the same time, like in the timed e2e region)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    x_dev2 = torch.empty_like(xd)
+
+    def copy_ms(h2d, d2h, reps=5):
+        sync_all()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s_in.wait_event(e0)
+            s_out.wait_event(e0)
+            if h2d:
+                with torch.cuda.stream(s_in):
+                    x_dev2.copy_(x_pin, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s_out):
+                    z_pin.copy_(zd, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_in)
+            torch.cuda.current_stream().wait_stream(s_out)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    h2d_bytes, d2h_bytes = x.numel() * 4, N_ROWS * K * 4
+    ms_h2d = reduce_scalar(copy_ms(True, False), dist.ReduceOp.MAX if world > 1 else None)
+    ms_d2h = reduce_scalar(copy_ms(False, True), dist.ReduceOp.MAX if world > 1 else None)
+    ms_both = reduce_scalar(copy_ms(True, True), dist.ReduceOp.MAX if world > 1 else None)
+    e2e_roofline = {
+        "h2d_gbs_per_rank": h2d_bytes / ms_h2d / 1e6, "d2h_gbs_per_rank": d2h_bytes / ms_d2h / 1e6,
+        "copies_only_ms_per_step": ms_both,
+        "aggregate_gbs": world * (h2d_bytes + d2h_bytes) / ms_both / 1e6,
+        "note": "pinned host memory, all {} rank(s) copying at once (slowest rank): the step's 16.8 MB of x "
+                "up and 67 MB of codes down, by themselves; e2e.ms_per_step cannot go below "
+                "max(kernel, copies) + the first wave's upload and the last wave's download".format(world)}
+
+    # ---- strong scaling: the ONE 65536-row batch row-sharded over the ranks (sparse_encode(group=)) ----
+    group = dist.group.WORLD if world > 1 else None
+    rows = N_ROWS // world
+    xs = xd[rank * rows:(rank + 1) * rows].contiguous()
+    zs = torch.empty(rows, K, device=dev)
+    gkw = {"group": group} if group is not None else {}
+
+    def strong_step(tol=0.0):
+        return sparse_encode(xs, wd, alpha=ALPHA, algorithm="ista", lr=lr, maxiter=MAXITER, tol=tol,
+                             path=path, out=zs, **gkw)
+
+    for _ in range(3):
+        strong_step()
+    ms_strong = timed(strong_step, args.steps)
+    strong_step(1e-9)
+    ms_strong_tol = timed(lambda: strong_step(1e-9), 3)
+    tile_rows = -(-rows // (148 * (-(-rows // (148 * 128)))))
+    strong = {
+        "value": args.steps * MAXITER / (ms_strong * 1e-3), "unit": UNIT, "rows_per_gpu": rows,
+        "ms_per_step": ms_strong / args.steps,
+        "ms_per_step_tol_1e-9": ms_strong_tol / 3,
+        "collectives_per_step": 0 if world == 1 else 1,
+        "note": "fixed total work: {} rows per GPU = {}-row tiles on M=128 MMAs ({} wave(s) of 148 SMs); "
+                "with a group the stop test is global: per-iteration sums recorded on chip, ONE all-reduce of "
+                "[maxiter + 1] doubles after the run (the sums and the element count), replay only if it fired early"
+                .format(rows, tile_rows, -(-rows // (148 * 128)))}
+
+    # ---- config 4: dict_learning, 131072 rows per rank, 100 inner iterations, ONE all-reduce per EM step ----
+    from lasso_b200.linear import dict_learning as dl_fn
+    from lasso_b200.testing import make_dictionary
+    dlmod = sys.modules["lasso_b200.linear.dict_learning"]
+    n4, inner, em_steps = 131072, 100, 10
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    w_true = make_dictionary(D, K, seed=123).to(dev)
+    code = torch.randn(n4, K, generator=gen, device=dev) * (torch.rand(n4, K, generator=gen, device=dev) < 0.05)
+    x4 = code @ w_true.T + 0.01 * torch.randn(n4, D, generator=gen, device=dev)
+    del code
+
+    def dl_run(steps):
+        torch.manual_seed(0)
+        return dl_fn(x4, K, alpha=ALPHA, steps=steps, device=str(dev), progbar=False, group=group,
+                     maxiter=inner, tol=0.0)
+
+    dl_run(2)
+    counts = {"all_reduce": 0, "broadcast": 0}
+    real_ar, real_bc = dist.all_reduce, dist.broadcast
+
+    def counted_ar(*a, **k):
+        counts["all_reduce"] += 1
+        return real_ar(*a, **k)
+
+    def counted_bc(*a, **k):
+        counts["broadcast"] += 1
+        return real_bc(*a, **k)
+
+    dlmod.PROFILE = {}
+    dist.all_reduce, dist.broadcast = counted_ar, counted_bc
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    w4, losses4 = dl_run(em_steps)
+    e1.record()
+    e1.synchronize()
+    dist.all_reduce, dist.broadcast = real_ar, real_bc
+    ms_dl = reduce_scalar(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+    ar_events = dlmod.PROFILE.get("all_reduce_events", [])
+    ar_us = 1e3 * sum(a.elapsed_time(b) for a, b in ar_events) / max(len(ar_events), 1)
+    ar_us = reduce_scalar(ar_us, dist.ReduceOp.MAX if world > 1 else None)
+    ar_bytes = dlmod.PROFILE.get("all_reduce_bytes", 0)
+    dlmod.PROFILE = None
+    dict_learning_c4 = {
+        "ms_per_em_step": ms_dl / em_steps, "rows_per_gpu": n4, "rows_total": n4 * world,
+        "inner_iterations": inner, "em_steps_timed": em_steps,
+        "fista_iters_per_s_aggregate": world * em_steps * inner / (ms_dl * 1e-3),
+        "all_reduce_us_per_step": ar_us if world > 1 else 0.0, "all_reduce_bytes": ar_bytes,
+        # minus the once-per-call reduction of the global row count
+        "all_reduces_per_em_step": (counts["all_reduce"] - 1) / em_steps if world > 1 else 0,
+        "broadcasts_per_call": counts["broadcast"],
+        "loss_first": float(losses4[0]), "loss_last": float(losses4[-1]),
+        "note": "BASELINE configs[3] per-GPU load (n = 1M at 8 GPUs): E-step on the resident kernel, Gram "
+                "statistics + loss sums + stop-test sums in ONE float64 buffer, one NCCL all-reduce, the "
+                "same atom sweep on every rank; all_reduce_us = CUDA events around that collective"}
+    del x4
+
+    # ---- the reference's loop as stock torch ops on this B200 (cuBLAS fp32, 13 launches + 1 sync / iteration) ----
+    gpu_eager = None
+    if world == 1:
+        fn, kind = reference_ista()
+        z0d = torch.zeros(N_ROWS, K, device=dev)
+        fn(xd, z0d, wd, alpha=ALPHA, fast=True, lr=lr, maxiter=20, tol=0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        z_eager = fn(xd, z0d, wd, alpha=ALPHA, fast=True, lr=lr, maxiter=MAXITER, tol=0.0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        device_step()
+        torch.cuda.synchronize()
+        gpu_eager = {"value": MAXITER / dt, "unit": UNIT, "kind": kind,
+                     "implementation": "lasso.linear.solvers.ista.ista on CUDA tensors (torch eager, cuBLAS fp32)",
+                     "rel_fro_ours_vs_eager": float((zd - z_eager).norm() / z_eager.norm())}
+        del z0d, z_eager
+
     if rank == 0:
         peaks = measured_peaks()
         iters_total = world * args.steps * MAXITER
         value = iters_total / (ms * 1e-3)
         e2e_value = world * e2e_steps * MAXITER / (ms_e2e * 1e-3)
-        path_name = {1: "ffma", 2: "tcgen05", 3: "resident"}[path_code]
+        path_name = {1: "ffma", 2: "tcgen05", 3: "resident", 4: "blocked"}[path_code]
         traffic = None
         summary = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(summary):
@@ -271,14 +447,19 @@ def run_ours(args, rank, local_rank, world):
             launch_us = ms * 1e3 / args.steps
             alg_flops = flops_per_it * MAXITER
             achieved = alg_flops / (launch_us * 1e-6) / 1e12
-            roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
-                        "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
+            # the launch is timed alone between L2 flushes: the burst figure is the denominator
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                        "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                        "fp32_grade_peak": peaks["bf16_tflops"] / 3.0,
+                        "frac_of_fp32_grade_peak": 3.0 * achieved / peaks["bf16_tflops"],
                         "traffic": traffic, "peak_source": peaks["source"],
                         "kernel": "fista_res_kernel (1 launch / {} iterations, state on chip)".format(MAXITER),
                         "launch_us": launch_us, "algorithmic_flops_per_launch": alg_flops,
                         "executed_mma_flops_per_launch": 3.0 * alg_flops,
-                        "note": "fp32-grade products need 3 fp16 MMAs each (h h', h l', l h'); "
-                                "peak is the measured dense bf16 rate sustained over a long kernel",
+                        "note": "frac = algorithmic flops (4 n d k per iteration) / measured dense bf16 BURST rate. "
+                                "The 1e-5 tolerance forbids single-pass fp16/bf16 products: every fp32-grade "
+                                "product costs 3 fp16 MMAs (h h', h l', l h'), so the reachable ceiling is "
+                                "fp32_grade_peak = peak / 3 and frac_of_fp32_grade_peak is the headroom figure",
                         "algorithmic_bytes_per_launch": N_ROWS * (D + K) * 4}
             l2_note = ("L2 flushed (256 MB memset) before every step, outside the per-step CUDA-event "
                        "intervals; a step reads x (16.8 MB) once and writes the codes (67 MB) once")
@@ -302,7 +483,9 @@ def run_ours(args, rank, local_rank, world):
                 "rows_per_gpu": N_ROWS, "iters_per_step": MAXITER,
                 "kernel_path": path_name,
                 "l2": l2_note,
-                "parallelism": "rows sharded, {} independent replica batches".format(world),
+                "parallelism": "value / e2e: one 65536-row batch per GPU (weak, no collective in the solve); "
+                               "strong: the one batch row-sharded over {} GPU(s); dict_learning_c4: 131072 rows "
+                               "per GPU, one all-reduce per EM step".format(world),
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": x.numel() * 4 + w.numel() * 4,
@@ -312,13 +495,18 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": roofline,
             "tensor_roofline": {"tflops": value / world * flops_per_it / 1e12,
-                                "peak_bf16_tflops": peaks["bf16_tflops_sustained"],
-                                "frac": value / world * flops_per_it / 1e12 / peaks["bf16_tflops_sustained"]},
+                                "peak_bf16_tflops": peaks["bf16_tflops"],
+                                "frac": value / world * flops_per_it / 1e12 / peaks["bf16_tflops"]},
+            "strong": strong,
+            "dict_learning_c4": dict_learning_c4,
+            "e2e_roofline": e2e_roofline,
         }
+        if gpu_eager is not None:
+            line["gpu_eager_baseline"] = gpu_eager
         if world == 1 and not args.no_cpu_baseline:
-            rate, iters, threads = cpu_reference_rate(x, w, lr)
+            rate, iters, threads, kind = cpu_reference_rate(x, w, lr)
             line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                "value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                 "sample": "{} FISTA iterations on the full 65536x64 batch after warm-up".format(iters)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -16,6 +16,12 @@
  *     themselves and return after the result is in the host buffer.
  *   - the caller owns every buffer passed in; the library owns only its private
  *     workspace (freed by lasso_b200_release_workspace or at process exit).
+ *   - the workspace is per device and shared by all callers: the entry points
+ *     that use it (the solves, lipschitz) take a per-device lock while they
+ *     enqueue, and a call on another stream first waits (on the device) for the
+ *     previous call's work, so calls from several threads / streams of one
+ *     device are serialised, never interleaved.  The _host entry point holds
+ *     the lock until its result is in the host buffer.
  *   - return value: 0 on success, negative lasso_b200_status on failure;
  *     lasso_b200_last_error() gives a thread-local message.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point
@@ -101,14 +107,16 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
 
 /*
  * Same solve on HOST buffers (pinned or pageable): copies x, weight (and z0)
- * to the current device, runs lasso_b200_fista_f32, copies the code back and
- * synchronises.  delta_hist, if given, is a HOST pointer here.
+ * to the current device, runs lasso_b200_fista_f32 on `stream`, copies the code
+ * back and synchronises the stream.  delta_hist, if given, is a HOST pointer here;
+ * z_out may alias z0.  (sparse_encode.py:38-73 called with CPU tensors; what
+ * dict_evaluate, dict_learning.py:16-20, does with held-out host data.)
  */
 int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const float* z0,
                                   float* z_out, int64_t n, int32_t d, int32_t k,
                                   double alpha, double lr, int32_t maxiter, int32_t fast,
                                   double tol_abs, int32_t* iters_done, double* delta_hist,
-                                  int32_t path);
+                                  int32_t path, void* stream);
 
 /*
  * Convolutional ISTA / FISTA -- replaces the loop of lasso/conv2d/ista.py:7-49 as
@@ -179,6 +187,15 @@ int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gr
                                         int32_t d, int32_t k, double eps,
                                         const float* redraw, int32_t* zeroed,
                                         int32_t positive, void* stream);
+
+/*
+ * z[:, j] = 0 for every atom j with mask[j] != 0 -- the in-place clearing of the codes of a
+ * re-drawn atom (dict_learning.py:98, `Z[:, k] = 0`) for all flagged atoms in one masked pass,
+ * so the host does not have to read the `zeroed` mask of lasso_b200_dict_update_gram_f32 back.
+ *   z      device [n,k] float32, updated in place      mask   device [k] int32
+ */
+int32_t lasso_b200_zero_columns_f32(float* z, int64_t n, int32_t k, const int32_t* mask,
+                                    void* stream);
 
 /*
  * Building blocks of the slow path of ista(): backtrack=True (Beck-Teboulle line search with

@@ -166,13 +166,28 @@ def _ridge(b, a, alpha):
     return torch.cholesky_solve(rhs, chol)
 
 
+def _lstsq(b, a):
+    # utils.py:13-25: QR least-norm solution when the system is under-determined (d < k),
+    # QR least-squares solution otherwise
+    m, n = a.shape[-2:]
+    if m < n:
+        q, r = torch.linalg.qr(a.transpose(-1, -2), mode='reduced')
+        d = torch.linalg.solve_triangular(r.transpose(-1, -2), b, upper=False)
+        return torch.matmul(q, d)
+    q, r = torch.linalg.qr(a, mode='reduced')
+    d = torch.matmul(q.transpose(-1, -2), b)
+    return torch.linalg.solve_triangular(r, d, upper=True)
+
+
 def initialize_code(x, weight, alpha, mode):
-    """sparse_encode.py:19-35 ('lstsq' left out: not on the ista path's defaults)."""
+    """sparse_encode.py:19-35."""
     n, k = x.size(0), weight.size(1)
     if mode == 'zero':
         return x.new_zeros(n, k)
     if mode == 'unif':
         return x.new(n, k).uniform_(-0.1, 0.1)
+    if mode == 'lstsq':
+        return _lstsq(x.T, weight).T
     if mode == 'ridge':
         return _ridge(x.T, weight, alpha).T
     if mode == 'transpose':

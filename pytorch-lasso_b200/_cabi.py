@@ -32,6 +32,7 @@ EXPORTS = (
     "lasso_b200_loss_terms_f32",
     "lasso_b200_gram_f32",
     "lasso_b200_dict_update_gram_f32",
+    "lasso_b200_zero_columns_f32",
     "lasso_b200_gradient_f32",
     "lasso_b200_linesearch_trial_f32",
     "lasso_b200_momentum_f32",
@@ -65,7 +66,7 @@ def _declare(lib):
                                          f64, c.POINTER(i32), vp, i32, vp]
     lib.lasso_b200_fista_f32_host.restype = i32
     lib.lasso_b200_fista_f32_host.argtypes = [vp, vp, vp, vp, i64, i32, i32, f64, f64, i32,
-                                              i32, f64, c.POINTER(i32), vp, i32]
+                                              i32, f64, c.POINTER(i32), vp, i32, vp]
     lib.lasso_b200_conv2d_fista_f32.restype = i32
     lib.lasso_b200_conv2d_fista_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32,
                                                 f64, f64, i32, i32, f64, c.POINTER(i32), vp, vp]
@@ -77,6 +78,8 @@ def _declare(lib):
     lib.lasso_b200_gram_f32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     lib.lasso_b200_dict_update_gram_f32.restype = i32
     lib.lasso_b200_dict_update_gram_f32.argtypes = [vp, vp, vp, i32, i32, f64, vp, vp, i32, vp]
+    lib.lasso_b200_zero_columns_f32.restype = i32
+    lib.lasso_b200_zero_columns_f32.argtypes = [vp, i64, i32, vp, vp]
     lib.lasso_b200_gradient_f32.restype = i32
     lib.lasso_b200_gradient_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.lasso_b200_linesearch_trial_f32.restype = i32
@@ -143,6 +146,16 @@ def select_path(n: int, d: int, k: int) -> int:
     return int(load().lasso_b200_select_path(n, d, k))
 
 
+def _check_out(out, n, k, device):
+    """A caller-provided result buffer is written through its raw pointer: it has to be exactly the
+    [n,k] float32 contiguous tensor on the right device."""
+    if tuple(out.shape) != (n, k) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 tensor of shape ({}, {})".format(n, k))
+    if out.device.type != device.type or (device.type == "cuda" and out.device != device):
+        raise ValueError("out must live on {}".format(device))
+    return out
+
+
 def fista_device(x, weight, z0, alpha, lr, maxiter, fast, tol_abs, path=PATH_AUTO,
                  want_iters=False, want_hist=False, out=None):
     """Run the FISTA loop on device tensors; returns (z, iters_done|None, hist|None)."""
@@ -155,7 +168,8 @@ def fista_device(x, weight, z0, alpha, lr, maxiter, fast, tol_abs, path=PATH_AUT
         raise LassoB200Error("weight must be [d,k] with d == x.shape[1]")
     if z0 is not None:
         z0 = _dev_f32(z0, "z0")
-    z = out if out is not None else torch.empty((n, k), dtype=torch.float32, device=x.device)
+    z = _check_out(out, n, k, x.device) if out is not None else \
+        torch.empty((n, k), dtype=torch.float32, device=x.device)
     hist = torch.zeros(max(maxiter, 1), dtype=torch.float64, device=x.device) if want_hist else None
     iters = ctypes.c_int32(0)
     with torch.cuda.device(x.device):
@@ -204,12 +218,15 @@ def fista_host(x, weight, z0, alpha, lr, maxiter, fast, tol_abs, path=PATH_AUTO,
     k = weight.shape[1]
     if z0 is not None:
         z0 = z0.contiguous()
-    z = out if out is not None else torch.empty((n, k), dtype=torch.float32)
+    z = _check_out(out, n, k, torch.device("cpu")) if out is not None else \
+        torch.empty((n, k), dtype=torch.float32)
     iters = ctypes.c_int32(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     _check(lib.lasso_b200_fista_f32_host(
         x.data_ptr(), weight.data_ptr(), z0.data_ptr() if z0 is not None else None,
         z.data_ptr(), n, d, k, float(alpha), float(lr), int(maxiter), int(bool(fast)),
-        float(tol_abs), ctypes.byref(iters) if want_iters else None, None, path_code(path)))
+        float(tol_abs), ctypes.byref(iters) if want_iters else None, None, path_code(path),
+        _stream_ptr(dev)))
     return z, (iters.value if want_iters else None)
 
 
@@ -224,13 +241,19 @@ def lipschitz(weight, iters=2000) -> float:
     return out.value
 
 
-def loss_terms(x, z, weight) -> torch.Tensor:
+def _f64_out(t, numel, name):
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == numel):
+        raise ValueError("{} must be a contiguous float64 CUDA tensor of {} elements".format(name, numel))
+    return t
+
+
+def loss_terms(x, z, weight, out=None) -> torch.Tensor:
     """Device tensor [2] float64: (sum (x - z W^T)^2, sum |z|)."""
     lib = load()
     x, z, weight = _dev_f32(x, "x"), _dev_f32(z, "z"), _dev_f32(weight, "weight")
     n, d = x.shape
     k = weight.shape[1]
-    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    out = _f64_out(out, 2, "out") if out is not None else torch.empty(2, dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
         _check(lib.lasso_b200_loss_terms_f32(x.data_ptr(), z.data_ptr(), weight.data_ptr(),
                                              n, d, k, out.data_ptr(), _stream_ptr(x.device)))
@@ -243,8 +266,10 @@ def gram(z, x, out_zz=None, out_zx=None):
     z, x = _dev_f32(z, "z"), _dev_f32(x, "x")
     n, k = z.shape
     d = x.shape[1]
-    gzz = out_zz if out_zz is not None else torch.empty((k, k), dtype=torch.float64, device=z.device)
-    gzx = out_zx if out_zx is not None else torch.empty((k, d), dtype=torch.float64, device=z.device)
+    gzz = _f64_out(out_zz, k * k, "out_zz") if out_zz is not None else \
+        torch.empty((k, k), dtype=torch.float64, device=z.device)
+    gzx = _f64_out(out_zx, k * d, "out_zx") if out_zx is not None else \
+        torch.empty((k, d), dtype=torch.float64, device=z.device)
     with torch.cuda.device(z.device):
         _check(lib.lasso_b200_gram_f32(z.data_ptr(), x.data_ptr(), n, d, k, gzz.data_ptr(),
                                        gzx.data_ptr(), _stream_ptr(z.device)))
@@ -266,6 +291,19 @@ def dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None, positive=Fals
             redraw.data_ptr() if redraw is not None else None, zeroed.data_ptr(),
             1 if positive else 0, _stream_ptr(dictionary.device)))
     return zeroed
+
+
+def zero_columns(z, mask):
+    """z[:, j] = 0 in place for every j with mask[j] != 0 (mask: int32 device tensor [k])."""
+    lib = load()
+    if not (z.is_cuda and z.dtype == torch.float32 and z.is_contiguous()):
+        raise LassoB200Error("z must be a contiguous float32 CUDA tensor")
+    n, k = z.shape
+    if not (mask.is_cuda and mask.dtype == torch.int32 and mask.numel() == k):
+        raise LassoB200Error("mask must be an int32 CUDA tensor of k entries")
+    with torch.cuda.device(z.device):
+        _check(lib.lasso_b200_zero_columns_f32(z.data_ptr(), n, k, mask.data_ptr(), _stream_ptr(z.device)))
+    return z
 
 
 def gradient(x, point, weight, grad_out=None):

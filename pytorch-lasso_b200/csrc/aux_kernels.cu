@@ -4,6 +4,8 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace lasso {
@@ -665,7 +667,25 @@ __global__ void __cluster_dims__(kSweepCluster, 1, 1) __launch_bounds__(kSweepCl
   cluster.sync();   // no CTA leaves while a peer may still store into its shared memory
 }
 
+// z[:, j] = 0 for every column whose mask entry is non-zero (dict_learning.py:98: the codes of a
+// re-drawn atom are cleared); masked so that the host never has to read the mask back
+__global__ void zero_columns_kernel(float* __restrict__ z, int64_t n, int k, const int* __restrict__ mask) {
+  const int64_t total = n * (int64_t)k, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    if (mask[(int)(i % k)]) z[i] = 0.f;
+}
+
 }  // namespace
+
+int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t st) {
+  if (n == 0) return LASSO_B200_OK;
+  const int64_t total = n * (int64_t)k;
+  const int blocks = (int)std::min<int64_t>((total + 1023) / 1024, 148 * 8);
+  zero_columns_kernel<<<blocks, 256, 0, st>>>(z, n, k, mask);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  return LASSO_B200_OK;
+}
 
 int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
                   cudaStream_t st) {
@@ -716,12 +736,9 @@ int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double 
   const size_t smem = sizeof(double) * ((size_t)kSweepDepth * (k + d) + d) +
                       sizeof(float) * ((size_t)d * k + k) + (size_t)k;
   if (smem <= 200 * 1024 && k <= 32 * kSweepMaxPerLane && (k % 2) == 0 && (d % 2) == 0 && k / 2 + d / 2 <= 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_smem_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    // per device (context) attribute: set on every launch, one process may drive several GPUs
+    LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_smem_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int threads = 1024;
     if (const char* t = getenv("LASSO_B200_SWEEP_THREADS")) threads = atoi(t);
     if (threads < 256 || threads > 1024 || (threads % 32) != 0 || k / 2 + d / 2 > threads) threads = 1024;
@@ -735,12 +752,8 @@ int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double 
   const size_t csmem = sizeof(double) * ((size_t)kSweepDepth * (k + dl) + dl + 2 * kSweepCluster) +
                        sizeof(float) * ((size_t)dl * k + k) + (size_t)k;
   if (redraw == nullptr && csmem <= 200 * 1024 && getenv("LASSO_B200_SWEEP_NO_CLUSTER") == nullptr) {
-    static bool cattr_set = false;
-    if (!cattr_set) {
-      LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_cluster_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      cattr_set = true;
-    }
+    LASSO_CUDA_TRY(cudaFuncSetAttribute((const void*)dict_sweep_cluster_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dict_sweep_cluster_kernel<<<kSweepCluster, kSweepClusterThreads, csmem, st>>>(dict, gzz, gzx, d, k, dl, eps,
                                                                                   zeroed, positive);
     LASSO_CHECK_LAUNCH();

@@ -33,6 +33,15 @@ struct Workspace {
   Buffer ctl;      // small scalars (int/double)
   Buffer scratch;  // Lipschitz Gram etc.
   Buffer hx, hw, hz;  // device copies for the _host entry points
+  // The workspace (and the per-device dictionary images / flags of the kernels) is shared by every
+  // caller of a device.  `mutex` serialises the host side of the entry points; `last_use` is recorded
+  // on the stream of the call that used it last, and a call on ANOTHER stream waits for it first, so
+  // solves issued from different streams or threads of one device run one after the other instead of
+  // overwriting each other's buffers.
+  std::mutex mutex;
+  cudaEvent_t last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
 };
 constexpr int kMaxDevices = 64;
 Workspace g_ws[kMaxDevices];
@@ -42,7 +51,6 @@ struct HostPipe {
   std::vector<cudaEvent_t> events;
 };
 HostPipe g_pipe[kMaxDevices];
-std::mutex g_ws_mutex;
 
 int ensure(Buffer& b, size_t bytes) {
   if (bytes <= b.bytes) return LASSO_B200_OK;
@@ -113,6 +121,52 @@ __global__ void select_result_kernel(const float* __restrict__ z_a, const float*
     z_out[i] = src[i];
 }
 
+// Scope of one entry point's use of the device workspace: locks the device's mutex, makes `st` wait
+// for the previous user if that was another stream, and records the hand-over event on exit.
+class Lease {
+ public:
+  Lease() = default;
+  Lease(const Lease&) = delete;
+  Lease& operator=(const Lease&) = delete;
+  int acquire(cudaStream_t st) {
+    int rc = current_workspace(&ws_);
+    if (rc) return rc;
+    ws_->mutex.lock();
+    locked_ = true;
+    st_ = st;
+    if (!ws_->last_use) {
+      cudaError_t e = cudaEventCreateWithFlags(&ws_->last_use, cudaEventDisableTiming);
+      if (e != cudaSuccess) {
+        set_error("cudaEventCreate failed: %s", cudaGetErrorString(e));
+        return LASSO_B200_ERR_CUDA;
+      }
+    }
+    if (ws_->used && ws_->last_stream != st) {
+      cudaError_t e = cudaStreamWaitEvent(st, ws_->last_use, 0);
+      if (e != cudaSuccess) {
+        set_error("cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+        return LASSO_B200_ERR_CUDA;
+      }
+    }
+    return LASSO_B200_OK;
+  }
+  Workspace* operator->() { return ws_; }
+  Workspace* get() { return ws_; }
+  ~Lease() {
+    if (!locked_) return;
+    if (ws_->last_use && cudaEventRecord(ws_->last_use, st_) == cudaSuccess) {
+      ws_->last_stream = st_;
+      ws_->used = true;
+    }
+    ws_->mutex.unlock();
+  }
+
+ private:
+  Workspace* ws_ = nullptr;
+  cudaStream_t st_ = nullptr;
+  bool locked_ = false;
+};
+
 int check_problem(const void* x, const void* w, const void* z_out, int64_t n, int d, int k) {
   if (n < 0 || d <= 0 || k <= 0) {
     set_error("invalid shape n=%lld d=%d k=%d", (long long)n, d, k);
@@ -149,6 +203,20 @@ int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k) {
   if (fista_tc_supported(n, d, k)) return LASSO_B200_PATH_TCGEN05;
   return fista_blk_supported(n, d, k) ? LASSO_B200_PATH_BLOCKED : LASSO_B200_PATH_FFMA;
 }
+
+}  // extern "C" (reopened below)
+
+namespace lasso {
+namespace {
+// body of lasso_b200_fista_f32; the caller holds the device's workspace lease
+int fista_device_impl(Workspace* ws, const float* x, const float* weight, const float* z0, float* z_out,
+                      int64_t n, int32_t d, int32_t k, double alpha, double lr, int32_t maxiter,
+                      int32_t fast, double tol_abs, int32_t* iters_done, double* delta_hist,
+                      int32_t path, cudaStream_t st);
+}  // namespace
+}  // namespace lasso
+
+extern "C" {
 
 int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z0, float* z_out,
                              int64_t n, int32_t d, int32_t k, double alpha, double lr,
@@ -188,10 +256,22 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
     return LASSO_B200_OK;
   }
 
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
-  Workspace* ws = nullptr;
-  rc = current_workspace(&ws);
-  if (rc) return rc;
+  Lease ws;
+  if ((rc = ws.acquire(st))) return rc;
+  return fista_device_impl(ws.get(), x, weight, z0, z_out, n, d, k, alpha, lr, maxiter, fast, tol_abs,
+                           iters_done, delta_hist, path, st);
+}
+
+}  // extern "C" (reopened below)
+
+namespace lasso {
+namespace {
+int fista_device_impl(Workspace* ws, const float* x, const float* weight, const float* z0, float* z_out,
+                      int64_t n, int32_t d, int32_t k, double alpha, double lr, int32_t maxiter,
+                      int32_t fast, double tol_abs, int32_t* iters_done, double* delta_hist,
+                      int32_t path, cudaStream_t st) {
+  int rc;
+  const size_t code_bytes = sizeof(float) * (size_t)n * (size_t)k;
   if ((rc = ensure(ws->code, code_bytes))) return rc;
   if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
   if ((rc = ensure(ws->ctl, 256))) return rc;
@@ -317,6 +397,10 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   return LASSO_B200_OK;
 }
 
+}  // namespace
+}  // namespace lasso
+
+extern "C" {
 
 int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, const float* z0, float* z_out,
                                     int64_t n_img, int32_t cin, int32_t h, int32_t w, int32_t kh, int32_t kw,
@@ -359,9 +443,8 @@ int32_t lasso_b200_conv2d_fista_f32(const float* x, const float* weight_lin, con
     if (iters_done) *iters_done = 0;
     return LASSO_B200_OK;
   }
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
-  Workspace* ws = nullptr;
-  int rc = current_workspace(&ws);
+  Lease ws;
+  int rc = ws.acquire(st);
   if (rc) return rc;
   if ((rc = ensure(ws->code, code_bytes))) return rc;
   if ((rc = ensure(ws->hist, sizeof(double) * (size_t)maxiter))) return rc;
@@ -429,12 +512,13 @@ namespace {
 // hist (device, [iters]) accumulates the stop-test record of all waves.  *fell_back = 1: an iterate
 // left the fp16 range somewhere; the caller must redo the batch on another path.
 constexpr int kPipeSlots = 3;
-int host_pipeline(const float* x, const float* z0, float* z_out, const float* dw, int64_t n, int d, int k,
-                  float lr_f, float lam_f, int iters, int fast, double* hist, int hist_mode, int* fell_back) {
+// `st` is the caller's stream (the solves run on it); the caller holds the workspace lease.
+int host_pipeline(Workspace* ws, const float* x, const float* z0, float* z_out, const float* dw, int64_t n,
+                  int d, int k, float lr_f, float lam_f, int iters, int fast, double* hist, int hist_mode,
+                  int* fell_back, cudaStream_t st) {
   int dev = 0, rc;
   LASSO_CUDA_TRY(cudaGetDevice(&dev));
   HostPipe& hp = g_pipe[dev];
-  cudaStream_t st = nullptr;
   if (!hp.s_in) {
     LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
     LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
@@ -442,16 +526,10 @@ int host_pipeline(const float* x, const float* z0, float* z_out, const float* dw
   const int64_t wave = fista_res_wave_rows(n), trows = fista_res_tile_rows(n);
   const int64_t nchunks = (n + wave - 1) / wave;
   const int slots = (int)std::min<int64_t>(kPipeSlots, nchunks);
-  float *dx, *dz;
-  {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Workspace* ws = nullptr;
-    if ((rc = current_workspace(&ws))) return rc;
-    if ((rc = ensure(ws->hx, sizeof(float) * (size_t)slots * wave * d))) return rc;
-    if ((rc = ensure(ws->hz, sizeof(float) * (size_t)slots * wave * k))) return rc;
-    dx = (float*)ws->hx.ptr;
-    dz = (float*)ws->hz.ptr;
-  }
+  if ((rc = ensure(ws->hx, sizeof(float) * (size_t)slots * wave * d))) return rc;
+  if ((rc = ensure(ws->hz, sizeof(float) * (size_t)slots * wave * k))) return rc;
+  float* dx = (float*)ws->hx.ptr;
+  float* dz = (float*)ws->hz.ptr;
   while ((int)hp.events.size() < 3 * kPipeSlots + 1) {
     cudaEvent_t ev;
     LASSO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -508,7 +586,8 @@ extern "C" {
 int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const float* z0,
                                   float* z_out, int64_t n, int32_t d, int32_t k, double alpha,
                                   double lr, int32_t maxiter, int32_t fast, double tol_abs,
-                                  int32_t* iters_done, double* delta_hist, int32_t path) {
+                                  int32_t* iters_done, double* delta_hist, int32_t path,
+                                  void* stream) {
   t_error[0] = 0;
   int rc = check_problem(x, weight, z_out, n, d, k);
   if (rc) return rc;
@@ -522,19 +601,16 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
   }
   const size_t xb = sizeof(float) * (size_t)n * d, wb = sizeof(float) * (size_t)d * k;
   const size_t zb = sizeof(float) * (size_t)n * k;
-  cudaStream_t st = nullptr;  // legacy default stream: ordered with the copies below
+  cudaStream_t st = (cudaStream_t)stream;
   int done = maxiter;
-  float* dw;
-  double* hist;
-  {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Workspace* ws = nullptr;
-    if ((rc = current_workspace(&ws))) return rc;
-    if ((rc = ensure(ws->hw, wb))) return rc;
-    if ((rc = ensure(ws->hist, sizeof(double) * (size_t)(maxiter + 1)))) return rc;
-    dw = (float*)ws->hw.ptr;
-    hist = (double*)ws->hist.ptr;
-  }
+  // the lease is held for the whole call (the entry point returns only after the codes are in the
+  // host buffer): two host threads on one device take turns
+  Lease ws;
+  if ((rc = ws.acquire(st))) return rc;
+  if ((rc = ensure(ws->hw, wb))) return rc;
+  if ((rc = ensure(ws->hist, sizeof(double) * (size_t)(maxiter + 1)))) return rc;
+  float* dw = (float*)ws->hw.ptr;
+  double* hist = (double*)ws->hist.ptr;
 
   const int resolved = path == LASSO_B200_PATH_AUTO ? lasso_b200_select_path(n, d, k) : path;
   if (resolved == LASSO_B200_PATH_RESIDENT && fista_res_supported(n, d, k) && maxiter > 0 &&
@@ -544,16 +620,25 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
     const int hist_mode = !need_hist ? 0 : ((delta_hist == nullptr && tol_abs == 0.0) ? 2 : 1);
     const float lr_f = (float)lr, lam_f = (float)(alpha * lr);
     LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
+    // z0 may alias z_out: a second pass (early stop) or the streaming fallback needs the start codes
+    // again after pass 1 has overwritten them
+    std::vector<float> z0_keep;
+    const float* z_start = z0;
+    if (z0 != nullptr && z0 == z_out) {
+      z0_keep.assign(z0, z0 + (size_t)n * k);
+      z_start = z0_keep.data();
+    }
     int fell_back = 0, run_iters = maxiter;
     for (int pass = 0; pass < 2; ++pass) {
-      if ((rc = host_pipeline(x, z0, z_out, dw, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
-                              need_hist ? hist : nullptr, hist_mode, &fell_back)))
+      if ((rc = host_pipeline(ws.get(), x, z_start, z_out, dw, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
+                              need_hist ? hist : nullptr, hist_mode, &fell_back, st)))
         return rc;
       if (fell_back || pass == 1 || tol_abs < 0.0 || run_iters <= 1) break;
       // the stop test is batch-global (ista.py:93): take it from the recorded sums and, if it fired
       // before maxiter, stream the batch through once more with exactly that many iterations
       std::vector<double> h((size_t)run_iters);
-      LASSO_CUDA_TRY(cudaMemcpy(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+      LASSO_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+      LASSO_CUDA_TRY(cudaStreamSynchronize(st));
       int stop = run_iters;
       for (int i = 0; i + 1 < run_iters; ++i)
         if (h[(size_t)i] <= tol_abs) {
@@ -566,7 +651,8 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
     if (!fell_back) {
       if (delta_hist) {
         std::vector<double> h((size_t)maxiter, 0.0);
-        LASSO_CUDA_TRY(cudaMemcpy(h.data(), hist, sizeof(double) * (size_t)run_iters, cudaMemcpyDeviceToHost));
+        LASSO_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * (size_t)run_iters, cudaMemcpyDeviceToHost, st));
+        LASSO_CUDA_TRY(cudaStreamSynchronize(st));
         memcpy(delta_hist, h.data(), sizeof(double) * (size_t)maxiter);
       }
       if (iters_done) *iters_done = run_iters;
@@ -574,27 +660,45 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
     }
     g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
     path = fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
+    if (z_start != z0) {
+      // restore the start codes the first pass overwrote
+      memcpy(z_out, z0_keep.data(), zb);
+    }
   }
 
   // plain copy - solve - copy (streaming kernels; whole batch on the device)
-  float *dx, *dz;
-  double* dh = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Workspace* ws = nullptr;
-    if ((rc = current_workspace(&ws))) return rc;
-    if ((rc = ensure(ws->hx, xb))) return rc;
-    if ((rc = ensure(ws->hz, zb + sizeof(double) * (size_t)(maxiter + 1)))) return rc;
-    dx = (float*)ws->hx.ptr;
-    dz = (float*)ws->hz.ptr;
-    if (delta_hist) dh = (double*)((char*)ws->hz.ptr + ((zb + 7) & ~(size_t)7));
-  }
+  if ((rc = ensure(ws->hx, xb))) return rc;
+  if ((rc = ensure(ws->hz, zb + sizeof(double) * (size_t)(maxiter + 1)))) return rc;
+  float* dx = (float*)ws->hx.ptr;
+  float* dz = (float*)ws->hz.ptr;
+  double* dh = delta_hist ? (double*)((char*)ws->hz.ptr + ((zb + 7) & ~(size_t)7)) : nullptr;
   LASSO_CUDA_TRY(cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, st));
   LASSO_CUDA_TRY(cudaMemcpyAsync(dw, weight, wb, cudaMemcpyHostToDevice, st));
   if (z0) LASSO_CUDA_TRY(cudaMemcpyAsync(dz, z0, zb, cudaMemcpyHostToDevice, st));
-  rc = lasso_b200_fista_f32(dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, maxiter, fast, tol_abs,
-                            &done, dh, path, st);
-  if (rc) return rc;
+  if (path == LASSO_B200_PATH_AUTO) path = lasso_b200_select_path(n, d, k);
+  if (maxiter == 0) {
+    if (z0 == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(dz, 0, zb, st));
+    done = 0;
+  } else {
+    if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05 && path != LASSO_B200_PATH_RESIDENT &&
+        path != LASSO_B200_PATH_BLOCKED) {
+      set_error("unknown path %d", path);
+      return LASSO_B200_ERR_INVALID;
+    }
+    if (!(lr > 0.0) || !std::isfinite(lr) || !std::isfinite(alpha)) {
+      set_error("invalid lr=%g / alpha=%g", lr, alpha);
+      return LASSO_B200_ERR_INVALID;
+    }
+    if ((path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) ||
+        (path == LASSO_B200_PATH_RESIDENT && !fista_res_supported(n, d, k)) ||
+        (path == LASSO_B200_PATH_BLOCKED && !fista_blk_supported(n, d, k))) {
+      set_error("tcgen05 paths do not take n=%lld d=%d k=%d", (long long)n, d, k);
+      return LASSO_B200_ERR_UNSUPPORTED;
+    }
+    rc = fista_device_impl(ws.get(), dx, dw, z0 ? dz : nullptr, dz, n, d, k, alpha, lr, maxiter, fast, tol_abs,
+                           &done, dh, path, st);
+    if (rc) return rc;
+  }
   LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, dz, zb, cudaMemcpyDeviceToHost, st));
   if (delta_hist && maxiter > 0)
     LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, dh, sizeof(double) * (size_t)maxiter,
@@ -617,9 +721,8 @@ int32_t lasso_b200_lipschitz_f32(const float* weight, int32_t d, int32_t k, int3
     return LASSO_B200_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
-  Workspace* ws = nullptr;
-  int rc = current_workspace(&ws);
+  Lease ws;
+  int rc = ws.acquire(st);
   if (rc) return rc;
   if ((rc = ensure(ws->scratch, sizeof(double) * ((size_t)m * m + 2 * (size_t)m + 8) + sizeof(float) * (2 * (size_t)m * m + 8))))
     return rc;
@@ -668,6 +771,15 @@ int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gr
   return dict_update_run(dict, gram_zz, gram_zx, d, k, eps, redraw, zeroed, positive ? 1 : 0, (cudaStream_t)stream);
 }
 
+int32_t lasso_b200_zero_columns_f32(float* z, int64_t n, int32_t k, const int32_t* mask, void* stream) {
+  t_error[0] = 0;
+  if (n < 0 || k <= 0 || !mask || (n > 0 && !z)) {
+    set_error("invalid argument to zero_columns");
+    return LASSO_B200_ERR_INVALID;
+  }
+  return zero_columns_run(z, n, k, mask, (cudaStream_t)stream);
+}
+
 int32_t lasso_b200_gradient_f32(const float* x, const float* point, const float* weight, int64_t n,
                                 int32_t d, int32_t k, float* grad, double* f_sum, void* stream) {
   t_error[0] = 0;
@@ -714,10 +826,11 @@ int32_t lasso_b200_momentum_f32(const float* z_next, const float* z, double beta
 }
 
 int32_t lasso_b200_release_workspace(void) {
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
   Workspace* ws = nullptr;
   int rc = current_workspace(&ws);
   if (rc) return rc;
+  std::lock_guard<std::mutex> lock(ws->mutex);
+  if (ws->used) cudaEventSynchronize(ws->last_use);   // nobody may still be running on the buffers
   Buffer* all[] = {&ws->code, &ws->hist, &ws->ctl, &ws->scratch, &ws->hx, &ws->hw, &ws->hz};
   for (Buffer* b : all) {
     if (b->ptr) cudaFree(b->ptr);

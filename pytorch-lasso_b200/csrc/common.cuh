@@ -147,6 +147,7 @@ int momentum_run(const float* z_next, const float* z, float beta, float* y, int6
                  double* delta, cudaStream_t st);
 int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz,
              double* gzx, cudaStream_t st);
+int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t st);
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
                     const float* redraw, int* zeroed, int positive, cudaStream_t st);
 

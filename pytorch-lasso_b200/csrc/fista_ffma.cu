@@ -404,12 +404,11 @@ template <int TM, int MODE, int BLK>
 int launch(const StepParams& p, cudaStream_t st) {
   const int num_sms = sm_count();
   const size_t smem = smem_bytes(TM, p.d, BLK);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // the attribute is per device (context): set it on every launch that needs more than the default
+  // 48 KB rather than caching a process-wide flag (one process may drive several GPUs)
+  if (smem > 48 * 1024)
     LASSO_CUDA_TRY(cudaFuncSetAttribute(fista_ffma_kernel<TM, MODE, BLK>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   int per_sm = 1;
   LASSO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
       &per_sm, fista_ffma_kernel<TM, MODE, BLK>, BLK * 4, smem));
@@ -424,18 +423,8 @@ int launch(const StepParams& p, cudaStream_t st) {
   return LASSO_B200_OK;
 }
 
-// Wide blocks (128 columns, 512 threads): tuning variant, LASSO_B200_FFMA_BLK=128.  Measured no better than
-// 64-column blocks: 21.97 vs 20.11 ms per 20 iterations at n=65536, d=289, k=300, and within the run-to-run
-// spread (115-132 EM steps/s) on the notebook configuration (n=10000), so it is never picked automatically.
-bool use_wide_blocks(const StepParams& p) {
-  if (smem_bytes(64, p.d, 128) > 200 * 1024) return false;
-  const char* e = getenv("LASSO_B200_FFMA_BLK");
-  return e != nullptr && atoi(e) == 128;
-}
-
 template <int MODE>
 int dispatch(const StepParams& p, cudaStream_t st) {
-  if (pick_tm(p.d) == 64 && use_wide_blocks(p)) return launch<64, MODE, 128>(p, st);
   switch (pick_tm(p.d)) {
     case 64: return launch<64, MODE, kBlk>(p, st);
     case 32: return launch<32, MODE, kBlk>(p, st);

@@ -570,8 +570,6 @@ fista_tc_kernel(const __grid_constant__ CUtensorMap tm_za, const __grid_constant
   if (warp == 1) tmem_dealloc(tbase, kTmemCols);
 }
 
-#include "fista_tc2.cuh"
-
 // dictionary [d][k] fp32 -> three bf16 piece images, each [k/64 slabs][64 rows][128 B] with
 // the 128-byte swizzle; zero padded to d = 64, k = 256.
 __global__ void prep_w_image_kernel(const float* __restrict__ w, int d, int k,
@@ -663,10 +661,8 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   if (trace_path && !S.trace) LASSO_CUDA_TRY(cudaMalloc(&S.trace, 32 * 512 * 8));
   if (S.trace) LASSO_CUDA_TRY(cudaMemsetAsync(S.trace, 0, 32 * 512 * 8, st));
   if (!S.attr_set) {
-    const void* kernels[8] = {(const void*)fista_tc_kernel<1>, (const void*)fista_tc_kernel<2>,
-                              (const void*)fista_tc_kernel<3>, (const void*)fista_tc_kernel<4>,
-                              (const void*)fista_tc2_kernel<1>, (const void*)fista_tc2_kernel<2>,
-                              (const void*)fista_tc2_kernel<3>, (const void*)fista_tc2_kernel<4>};
+    const void* kernels[4] = {(const void*)fista_tc_kernel<1>, (const void*)fista_tc_kernel<2>,
+                              (const void*)fista_tc_kernel<3>, (const void*)fista_tc_kernel<4>};
     for (const void* kfn : kernels)
       LASSO_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     S.attr_set = true;
@@ -678,11 +674,7 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   // Tile height: the smallest multiple of 8 rows for which the tiles still fit the same number
   // of waves as 128-row tiles would need -- the last wave is then (almost) full instead of
   // leaving SMs idle (n = 65536 on 148 SMs: 592 slots, 111 -> 112 rows, 586 tiles).
-  // kernel version: 1 = single tile per SM with a y master in TMEM (default, faster at <= 4 tiles per
-  // SM), 2 = two tiles in flight per SM (LASSO_B200_TC_VERSION=2)
-  const char* ver_env = getenv("LASSO_B200_TC_VERSION");
-  const int version = (ver_env && ver_env[0] == '2') ? 2 : 1;
-  const int64_t slots = (int64_t)S.num_sms * version;
+  const int64_t slots = (int64_t)S.num_sms;
   const int64_t waves = ((a.n + kTileM - 1) / kTileM + slots - 1) / slots;
   int64_t tile_rows = (a.n + waves * slots - 1) / (waves * slots);
   tile_rows = ((tile_rows + 7) / 8) * 8;
@@ -697,7 +689,7 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   int64_t h[2] = {tile_rows, tile_rows};
   int stagger = 0;
   const char* st_env = getenv("LASSO_B200_STAGGER");
-  if (version == 1 && waves >= 2 && grid == (unsigned)S.num_sms) {
+  if (waves >= 2 && grid == (unsigned)S.num_sms) {
     stagger = st_env ? atoi(st_env) : 12000;   // swept on B200 at C2: 0 -> 56.3 us, 8k -> 54.0, 12k -> 51.6, 16k -> 56.9
     // one row costs ~80 cycles of a tile's HBM share: take stagger / (waves * 80) rows off the
     // late class per tile and give them to the early class
@@ -720,8 +712,8 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
   const int64_t region_a = n_even * waves * h[0];
   CUtensorMap tm_za, tm_zb, tm_za1, tm_zb1;
   int rc;
-  if ((rc = make_map(&tm_za, a.z_a, a.n, a.k, (int)(version == 1 ? h[0] : tile_rows)))) return rc;
-  if ((rc = make_map(&tm_zb, a.z_b, a.n, a.k, (int)(version == 1 ? h[0] : tile_rows)))) return rc;
+  if ((rc = make_map(&tm_za, a.z_a, a.n, a.k, (int)h[0]))) return rc;
+  if ((rc = make_map(&tm_zb, a.z_b, a.n, a.k, (int)h[0]))) return rc;
   if ((rc = make_map(&tm_za1, a.z_a, a.n, a.k, (int)h[1]))) return rc;
   if ((rc = make_map(&tm_zb1, a.z_b, a.n, a.k, (int)h[1]))) return rc;
 
@@ -775,9 +767,7 @@ int fista_tc_run(const FistaArgs& a, float* /*z_out*/, cudaStream_t st) {
     const int dsteps = (a.d + 15) / 16;
 #define LASSO_TC_LAUNCH(DS)                                                                \
   do {                                                                                     \
-    if (version == 1)                                                                      \
-      fista_tc_kernel<DS><<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, tm_za1, tm_zb1, p);   \
-    else fista_tc2_kernel<DS><<<grid, kThreads2, kSmemBytes, st>>>(tm_za, tm_zb, p);              \
+    fista_tc_kernel<DS><<<grid, kThreads, kSmemBytes, st>>>(tm_za, tm_zb, tm_za1, tm_zb1, p);     \
   } while (0)
     switch (dsteps) {
       case 1: LASSO_TC_LAUNCH(1); break;

@@ -94,33 +94,35 @@ def solve(x, z0, weight, alpha=1.0, fast=True, lr='auto', maxiter=10, tol=1e-5,
     lr = float(lr)
     alpha = float(alpha)
     sharded = group is not None and torch.distributed.get_world_size(group) > 1
-    numel = n * k
-    if sharded:
-        cnt = torch.tensor([numel], dtype=torch.int64, device=x.device)
-        torch.distributed.all_reduce(cnt, group=group)
-        numel = int(cnt.item())
-    tol_abs = _abs_tolerance(numel, tol)
 
     if not x.is_cuda:
         if sharded:
             raise NotImplementedError("sharded solves need CUDA tensors")
-        z, iters = _cabi.fista_host(x, weight, z0, alpha, lr, maxiter, fast, tol_abs,
+        z, iters = _cabi.fista_host(x, weight, z0, alpha, lr, maxiter, fast, _abs_tolerance(n * k, tol),
                                     path=path, want_iters=return_iters, out=out)
         return (z, iters) if return_iters else z
 
     if not sharded or maxiter <= 1:
-        z, iters, _ = _cabi.fista_device(x, weight, z0, alpha, lr, maxiter, fast, tol_abs,
+        z, iters, _ = _cabi.fista_device(x, weight, z0, alpha, lr, maxiter, fast, _abs_tolerance(n * k, tol),
                                          path=path, want_iters=return_iters, out=out)
         return (z, iters) if return_iters else z
 
     # Row-sharded batch: run all iterations with the local test disabled, make the
-    # per-iteration deltas global with ONE all-reduce, and replay a shorter run in
-    # the (rare) case the global test fired early.  Deterministic kernels make the
+    # per-iteration deltas global with ONE all-reduce (the shard's element count, which the
+    # threshold z0.numel() * tol of ista.py:64 needs globally, rides in the same buffer), and replay a
+    # shorter run in the (rare) case the global test fired early.  Deterministic kernels make the
     # replay identical to stopping in place (ista.py:93-95 semantics).
     z, _, hist = _cabi.fista_device(x, weight, z0, alpha, lr, maxiter, fast, -1.0,
                                     path=path, want_hist=True, out=out)
-    torch.distributed.all_reduce(hist, group=group)
-    done = _first_stop(hist, tol_abs)
+    buf = torch.cat([hist, hist.new_tensor([float(n * k)])])
+    torch.distributed.all_reduce(buf, group=group)
+    host = buf.tolist()                                   # the solve's one read-back
+    tol_abs = _abs_tolerance(int(round(host[-1])), tol)
+    done = maxiter
+    for i, delta in enumerate(host[:maxiter - 1]):
+        if delta <= tol_abs:
+            done = i + 1
+            break
     if done < maxiter:
         z, _, _ = _cabi.fista_device(x, weight, z0, alpha, lr, done, fast, -1.0, path=path,
                                      out=out)

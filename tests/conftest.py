@@ -39,6 +39,10 @@ SOLVER_CASES = [
     "ista_ragged", "ista_wide_d", "ista_earlystop", "ista_earlystop_plain",
     "ista_one_iter", "ista_big_alpha", "ista_warmstart",
     "encode_init_zero", "encode_init_ridge", "encode_init_transpose",
+    # round 2: shapes that reach the k-blocked tcgen05 kernel, the notebook's dictionary, the two
+    # remaining initialisers (z0 of the fixture is the reference's start code)
+    "r2_blocked_128x512", "r2_blocked_64x512_plain", "r2_notebook_289x300",
+    "r2_encode_init_lstsq", "r2_encode_init_unif",
 ]
 
 

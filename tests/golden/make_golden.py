@@ -53,7 +53,11 @@ def main():
     ref, ref_ista = import_reference()
     out = {}
 
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # fixture-name prefixes to (re)write
+
     def save(name, **arrays):
+        if only and not any(name.startswith(o) for o in only):
+            return
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v))
                                      for k, v in arrays.items()})
@@ -203,6 +207,71 @@ def main():
                                           lambd=1e-2, progbar=False, algorithm="ista", maxiter=10)
         save("dict_learning_" + ("constrained" if constrained else "ridge"), x=x, weight0=w0,
              weight=w_fin, losses=losses, alpha=0.5, steps=8, lambd=1e-2, maxiter=10)
+
+    # ---- round 2 additions -----------------------------------------------------------------
+    # shapes that reach the k-blocked tcgen05 kernel (d <= 128, k <= 1024 beyond the resident shape) and
+    # the notebook's dictionary (d = 289, k = 300: examples/dict_learning_omniglot.ipynb:638-640)
+    for name, n, d, k, kind, alpha, opts in [
+            ("r2_blocked_128x512", 160, 128, 512, "planted", 0.05, dict(fast=True, maxiter=100, tol=0.0)),
+            ("r2_blocked_64x512_plain", 130, 64, 512, "randn", 0.1, dict(fast=False, maxiter=40, tol=0.0)),
+            ("r2_notebook_289x300", 96, 289, 300, "planted", 0.5, dict(fast=True, maxiter=20, tol=0.0))]:
+        x, w = make_problem(n, d, k, seed=len(name), kind=kind)
+        lr = 1.0 / lipschitz64(w)
+        z0 = torch.zeros(n, k)
+        z = ref_ista(x, z0, w, alpha=alpha, lr=lr, **opts)
+        save(name, x=x, weight=w, z0=z0, z=z, alpha=alpha, lr=lr,
+             fast=int(opts["fast"]), maxiter=opts["maxiter"], tol=opts["tol"])
+
+    # init='lstsq' (sparse_encode.py:26-27, utils.py:13-25: least-norm branch since d < k)
+    x, w = make_problem(64, 10, 50, seed=5, kind="randn")
+    lr = 1.0 / lipschitz64(w)
+    z = ref.sparse_encode(x, w, alpha=0.5, algorithm="ista", init="lstsq", lr=lr, maxiter=12, tol=0.0)
+    z0 = ref.initialize_code(x, w, 0.5, "lstsq")
+    save("r2_encode_init_lstsq", x=x, weight=w, z0=z0, z=z, alpha=0.5, lr=lr, fast=1, maxiter=12, tol=0.0)
+    # init='unif' (sparse_encode.py:24-25) draws from the global CPU generator
+    torch.manual_seed(4321)
+    z = ref.sparse_encode(x, w, alpha=0.5, algorithm="ista", init="unif", lr=lr, maxiter=12, tol=0.0)
+    torch.manual_seed(4321)
+    z0 = ref.initialize_code(x, w, 0.5, "unif")
+    save("r2_encode_init_unif", x=x, weight=w, z0=z0, z=z, alpha=0.5, lr=lr, fast=1, maxiter=12, tol=0.0,
+         seed=4321)
+
+    # backtracking that FAILS (ista.py:39-52): eta so close to 1 that 1000 shrinks of a far too large
+    # step never satisfy F <= Q -> warning, revert to the initial step for this iteration
+    x, w = make_problem(24, 6, 12, seed=13, kind="randn")
+    lr = 1e6 / lipschitz64(w)
+    z0 = torch.zeros(24, 12)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        z = ref_ista(x, z0, w, alpha=0.2, lr=lr, fast=True, maxiter=2, tol=0.0, backtrack=True,
+                     eta_backtrack=1.0 + 1e-6)
+    assert any("backtracking line search failed" in str(c.message) for c in caught)
+    save("r2_backtrack_failure", x=x, weight=w, z0=z0, z=z, alpha=0.2, lr=lr, fast=1, maxiter=2, tol=0.0,
+         backtrack=1, eta_backtrack=1.0 + 1e-6)
+
+    # dict_learning with the step PINNED (lr travels through **solver_kwargs, dict_learning.py:25,38):
+    # bit-reproducible reference, so the CUDA path is held to 1e-5 on W and 1e-6 on the losses
+    for constrained in (True, False):
+        x, _ = make_problem(128, 10, 50, seed=21, kind="randn")
+        torch.manual_seed(0)
+        w0 = torch.empty(10, 50)
+        torch.nn.init.orthogonal_(w0)
+        if constrained:
+            w0 = torch.nn.functional.normalize(w0, dim=0)
+        torch.manual_seed(0)
+        w_fin, losses = ref.dict_learning(x, 50, alpha=0.5, constrained=constrained, steps=8,
+                                          lambd=1e-2, progbar=False, algorithm="ista", maxiter=10, lr=0.05)
+        save("r2_dict_learning_pinned_" + ("constrained" if constrained else "ridge"), x=x, weight0=w0,
+             weight=w_fin, losses=losses, alpha=0.5, steps=8, lambd=1e-2, maxiter=10, lr=0.05)
+    # ... and with persist=True + init='ridge' (what the notebook runs, ipynb:638-640)
+    x, _ = make_problem(128, 10, 50, seed=22, kind="planted")
+    torch.manual_seed(0)
+    w0 = torch.nn.functional.normalize(torch.nn.init.orthogonal_(torch.empty(10, 50)), dim=0)
+    torch.manual_seed(0)
+    w_fin, losses = ref.dict_learning(x, 50, alpha=0.2, constrained=True, persist=True, steps=6,
+                                      progbar=False, algorithm="ista", init="ridge", maxiter=8, lr=0.05)
+    save("r2_dict_learning_persist_ridge_init", x=x, weight0=w0, weight=w_fin, losses=losses, alpha=0.2,
+         steps=6, maxiter=8, lr=0.05)
 
     for name, size in sorted(out.items()):
         print("{:32s} {:8d} bytes".format(name, size))

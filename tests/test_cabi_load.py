@@ -63,3 +63,18 @@ def test_missing_library_raises(build_extension, monkeypatch):
     monkeypatch.setattr(cabi, "LIB_PATH", os.path.join(ROOT, "does", "not", "exist.so"))
     with pytest.raises(cabi.LassoB200Error):
         cabi.load()
+
+
+def test_integration_stub_compiles_and_binds_declared_symbols():
+    """The ctypes stub of INTEGRATION.md section B must at least compile and only name exported symbols
+    (it is executed on the GPU by tests/test_gpu_parity.py::test_integration_stub_runs_as_written)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "ctypes.CDLL" in b]
+    assert len(blocks) == 1
+    compile(blocks[0], "INTEGRATION.md", "exec")
+    from lasso_b200 import _cabi
+    for sym in set(re.findall(r"_lib\.(lasso_b200_\w+)", blocks[0])):
+        assert sym in _cabi.EXPORTS, sym

@@ -160,9 +160,19 @@ class _FakeCuda(torch.Tensor):
         return True
 
 
-def _stub_gram(z, x):
+def _stub_gram(z, x, out_zz=None, out_zx=None):
     z64, x64 = torch.Tensor(z).double(), torch.Tensor(x).double()
-    return z64.T @ z64, z64.T @ x64
+    gzz, gzx = z64.T @ z64, z64.T @ x64
+    if out_zz is not None:
+        out_zz.copy_(gzz)
+        out_zx.copy_(gzx)
+        return out_zz, out_zx
+    return gzz, gzx
+
+
+def _stub_zero_columns(z, mask):
+    torch.Tensor(z)[:, mask.bool()] = 0
+    return z
 
 
 def _stub_dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None, positive=False):
@@ -174,9 +184,13 @@ def _stub_dict_update_gram(dictionary, gzz, gzx, eps=1e-10, redraw=None, positiv
     return mask
 
 
-def _stub_loss_terms(x, z, w):
+def _stub_loss_terms(x, z, w, out=None):
     x, z, w = torch.Tensor(x).double(), torch.Tensor(z).double(), torch.Tensor(w).double()
-    return torch.stack([(z @ w.T - x).square().sum(), z.abs().sum()])
+    terms = torch.stack([(z @ w.T - x).square().sum(), z.abs().sum()])
+    if out is not None:
+        out.copy_(terms)
+        return out
+    return terms
 
 
 def _mstep_problem():
@@ -196,14 +210,17 @@ def _mstep_worker(rank, world, port, result_dir):
         pkg._cabi.gram = _stub_gram
         pkg._cabi.dict_update_gram = _stub_dict_update_gram
         pkg._cabi.loss_terms = _stub_loss_terms
+        pkg._cabi.zero_columns = _stub_zero_columns
         x, w, z = _mstep_problem()
         rows = slice(0, 40) if rank == 0 else slice(40, 96)          # ragged shards
-        xs, zs = x[rows].clone(), z[rows].clone()
+        xs, zs = x[rows].clone().as_subclass(_FakeCuda), z[rows].clone().as_subclass(_FakeCuda)
+        w = w.as_subclass(_FakeCuda)
         torch.manual_seed(100 + rank)                                 # ranks draw differently: rank 0's draw wins
-        d_new = update_dict(w.clone().as_subclass(_FakeCuda), xs, zs, group=dist.group.WORLD)
+        d_new = update_dict(torch.Tensor(w).clone().as_subclass(_FakeCuda), xs, zs, group=dist.group.WORLD)
         v_new = update_dict_ridge(xs, zs, lambd=1e-2, group=dist.group.WORLD)
         loss = lasso_loss(xs, zs, w, 0.05, group=dist.group.WORLD)
-        torch.save({"d": torch.Tensor(d_new).clone(), "v": v_new, "loss": float(loss), "z5": float(zs[:, 5].abs().max())},
+        torch.save({"d": torch.Tensor(d_new).clone(), "v": torch.Tensor(v_new).clone(), "loss": float(loss),
+                    "z5": float(torch.Tensor(zs)[:, 5].abs().max())},
                    os.path.join(result_dir, "m%d.pt" % rank))
     finally:
         dist.destroy_process_group()
@@ -223,3 +240,67 @@ def test_sharded_mstep_two_ranks(tmp_path):
     assert abs(float(parts[0]["d"][:, 5].norm()) - 1.0) <= 1e-6 and parts[0]["z5"] == 0.0
     assert rel_fro(parts[0]["v"], oracle.update_dict_ridge(x, z, lambd=1e-2)) <= 1e-5
     assert abs(parts[0]["loss"] - float(oracle.lasso_loss(x, z, w, 0.05))) <= 1e-6 * abs(parts[0]["loss"])
+
+
+# ---------------------------------------------------------------------------------------
+# 2-rank gloo: a whole sharded dict_learning step is ONE all-reduce (statistics, loss sums and the
+# E-step's stop-test sums in one buffer) and reproduces the unsharded run
+# ---------------------------------------------------------------------------------------
+
+def _dl_worker(rank, world, port, tol, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import lasso_b200 as pkg
+        dl = __import__("sys").modules["lasso_b200.linear.dict_learning"]
+        pkg._cabi.fista_device = _oracle_backed_fista_device
+        pkg._cabi.gram = _stub_gram
+        pkg._cabi.dict_update_gram = _stub_dict_update_gram
+        pkg._cabi.loss_terms = _stub_loss_terms
+        pkg._cabi.zero_columns = _stub_zero_columns
+        dl.default_device = lambda: torch.device("cpu")
+        calls = {"all_reduce": 0, "broadcast": 0}
+        real_ar, real_bc = dist.all_reduce, dist.broadcast
+
+        def counted_ar(*a, **k):
+            calls["all_reduce"] += 1
+            return real_ar(*a, **k)
+
+        def counted_bc(*a, **k):
+            calls["broadcast"] += 1
+            return real_bc(*a, **k)
+        dist.all_reduce, dist.broadcast = counted_ar, counted_bc
+        x, _ = make_problem(96, 12, 24, seed=5, kind="planted")
+        rows = slice(0, 40) if rank == 0 else slice(40, 96)
+        torch.manual_seed(0)
+        steps = 4
+        w, losses = dl.dict_learning(x[rows].clone(), 24, alpha=0.05, steps=steps, progbar=False, lr=0.1,
+                                     maxiter=30, tol=tol, group=dist.group.WORLD)
+        torch.save({"w": w, "losses": losses, "calls": calls, "steps": steps},
+                   os.path.join(result_dir, "d%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tol", [0.0, 3e-3])
+def test_sharded_dict_learning_one_all_reduce_per_step(tmp_path, tol):
+    port = _free_port()
+    mp.spawn(_dl_worker, args=(2, port, tol, str(tmp_path)), nprocs=2, join=True)
+    parts = [torch.load(os.path.join(str(tmp_path), "d%d.pt" % r)) for r in range(2)]
+    assert torch.equal(parts[0]["w"], parts[1]["w"]) and torch.equal(parts[0]["losses"], parts[1]["losses"])
+    steps = parts[0]["steps"]
+    x, _ = make_problem(96, 12, 24, seed=5, kind="planted")
+    torch.manual_seed(0)
+    want_w, want_losses = oracle.dict_learning(x, 24, alpha=0.05, steps=steps, lr=0.1, maxiter=30, tol=tol)
+    assert rel_fro(parts[0]["w"], want_w) <= 1e-4
+    assert torch.allclose(parts[0]["losses"], want_losses, rtol=1e-4)
+    # one all-reduce for the global row count + one per EM step; with tol > 0 a step whose global stop
+    # test fired early is redone once (a second all-reduce for that step); one broadcast of the
+    # initial dictionary, none afterwards (no degenerate atoms here)
+    n_ar = parts[0]["calls"]["all_reduce"]
+    if tol == 0.0:
+        assert n_ar == 1 + steps
+    else:
+        assert 1 + steps <= n_ar <= 1 + 2 * steps
+    assert parts[0]["calls"]["broadcast"] == 1
