@@ -15,14 +15,14 @@
 //             An iterate that would overflow fp16 anyway ends as inf / NaN, raises a flag at
 //             the final store and the caller re-runs the batch with the streaming bf16x3 kernel.
 //   state     z_i  : shared memory, 128 x 256 fp32, XOR-swizzled rows (128 KB)
-//             y_i  : TMEM columns [0,256) fp32 (the momentum point, ista.py:100)
+//             y_i  : TMEM, fp32 (the momentum point, ista.py:100): 192 columns + 16 registers per thread
 //             x    : shared memory 128 x 64 fp32 (32 KB);  dictionary pieces: 64 KB
-//   per iteration (one tile, 16 compute warps = 4 groups of 128 rows, 1 MMA warp):
-//     A   y chunk (32 atoms) -> pieces -> TMEM stage           | GEMM1  R = Y W^T  (TS MMAs,
-//     B   r = (R_big + R_small) - x -> pieces -> TMEM          |         B = resident W, K-major)
-//     C   z+ = softshrink(y - lr g, lam) (ista.py:90), delta,  | GEMM2  G = r W per 64 atoms
-//         y+ = z+ + beta (z+ - z) (ista.py:100), in place      |         (same image, MN-major)
-//   TMEM columns: y 256 | piece stages 2 x 32 | r pieces 64 | acc0 64 | acc1 64 = 512.
+//   per iteration (one tile; 16 compute warps in two sets of 8, 1 MMA warp):
+//     B   r = R - x -> fp16 pieces, written over R (in place)   | GEMM1  R = Y W^T  (TS MMAs,
+//     C   z+ = softshrink(y - lr g, lam) (ista.py:90), delta,   |         B = resident W, K-major)
+//         y+ = z+ + beta (z+ - z) (ista.py:100), in place,      | GEMM2  G = r W per 64 atoms
+//         pieces of y+ -> slot of the chunk's set               |         (same image, MN-major)
+//   TMEM columns: y 192 | S 64 | Q 64 | R / r pieces 64 | G0 64 | G1 64 = 512 (see the kernel).
 //   The stop test (ista.py:93) cannot be taken mid-run (it is a batch-global sum): every
 //   iteration's sum goes to hist[] and the caller replays a shorter run when it fired early.
 #include <cuda.h>
@@ -55,10 +55,10 @@ constexpr uint32_t kSmemZ = kSmemW + kWBytes;              // [128][256] fp32, 1
 constexpr uint32_t kSmemX = kSmemZ + kTileM * kKP * 4;     // [128][64] fp32, 256 B rows
 constexpr uint32_t kSmemBytesR = kSmemX + kTileM * kDP * 4;   // 229376
 
-constexpr uint32_t kColY = 0;         // y chunks 0..2, fp32 (chunk 3: registers)
+constexpr uint32_t kColY = 0;         // y, fp32: chunks 0, 1 and half of chunks 2, 3 (the rest: registers)
 constexpr uint32_t kColS = 192;       // piece slot S: [h 32 cols][l 32 cols] = 64 atoms of y (even chunks)
-constexpr uint32_t kColQ = 256;       // r pieces [h 32][l 32] = 64 features during GEMM2, then the slot of the odd chunks
-constexpr uint32_t kColAccR = 320;    // R = Y W^T (GEMM1)
+constexpr uint32_t kColQ = 256;       // piece slot Q (odd chunks)
+constexpr uint32_t kColAccR = 320;    // R = Y W^T (GEMM1); phase B overwrites it with the pieces of r [h 32][l 32]
 constexpr uint32_t kColAccG = 384;    // G = r W, two buffers of one 64-atom chunk (GEMM2)
 constexpr uint32_t kTmemCols = 512;
 
@@ -118,9 +118,11 @@ __device__ __noinline__ void res_wait_spin(uint32_t addr, uint32_t par, volatile
     __trap();
   }
 }
-#define RES_WAIT(bar, parity)                                                             \
+#define RES_WAIT(bar, parity) RES_WAIT_A(smem_u32(bar), parity)
+// the same on a precomputed shared-memory address
+#define RES_WAIT_A(addr, parity)                                                          \
   do {                                                                                    \
-    const uint32_t _addr = smem_u32(bar), _par = (parity) & 1u;                           \
+    const uint32_t _addr = (addr), _par = (parity) & 1u;                                  \
     uint32_t _ok;                                                                         \
     asm volatile(                                                                         \
         "{\n\t.reg .pred P;\n\t"                                                         \
@@ -250,30 +252,36 @@ __device__ __noinline__ bool res_store_tile(const ResParams& p, const uint8_t* z
   return bad;
 }
 
-// Schedule of one iteration (NQ = 4 chunks of 64 atoms; all 16 compute warps work on the same
-// chunk, each thread on 16 atoms of one row):
+// Schedule of one iteration (NQ = 4 chunks of 64 atoms).  The 16 compute warps form two sets of
+// 8 (4 TMEM lane quadrants x 2 column halves): set A runs the even chunks, set B the odd ones, a
+// thread works on 32 atoms of one row in two sub-steps of 16.  Every SM sub-partition hosts two warps
+// of each set, and the sets are out of phase by one GEMM2 chunk, so one set's TMEM / barrier
+// latencies hide behind the other set's arithmetic (all 16 warps in lock step left the ALUs idle
+// for ~40 % of a chunk):
 //
 //   MMA warp   GEMM2 q0 | q1 | q2 | q3 | G1' q0 | G1' q1 | G1' q2 | G1' q3 ........ (B) GEMM2 q0 | q1
-//   compute        C(0)      |    C(1)     |    C(2)     |    C(3)     | idle |  B  | idle
+//   set A          C(0)           |      C(2)           | idle            |  B  |
+//   set B               C(1)           |      C(3)           | idle       |  B  |
 //
 // C(q): z+ = softshrink(y - lr g, lam), stop-test record, y+ = z+ + beta (z+ - z) in place, then
 // the fp16 pieces of y+ go to a piece slot, where slice q of the NEXT iteration's GEMM1 (G1')
-// picks them up.  The tensor pipe is the busier side (96 MMAs ~ 4.1 k cycles per iteration against
-// ~3.4 k issue cycles of epilogue), so the MMA queue must never wait on the epilogue:
-//   * G has two buffers: GEMM2 q+1 runs while C(q) drains buffer q & 1, GEMM2 q+2 starts as soon as
-//     C(q) has the accumulator in registers;
-//   * the pieces have two slots: even chunks go to S, odd chunks to Q -- the columns that hold the
-//     pieces of r during GEMM2 and are dead once GEMM2 q3 has completed;
-//   * the 64 columns this needs come from y: chunk 3 of y lives in registers (16 per thread).
-// TMEM columns: y chunks 0-2 192 | S 64 | Q (r pieces / odd slots) 64 | R 64 | G0 64 | G1 64 = 512.
+// picks them up.  The tensor pipe is the busier side (96 MMAs ~ 4.1 k cycles per iteration), so
+// its queue must never wait on the epilogue:
+//   * G has two buffers, one per set: GEMM2 q+2 starts as soon as C(q) has the accumulator in registers;
+//   * the pieces have two slots, one per set (S: even chunks, Q: odd chunks);
+//   * the pieces of r overwrite the accumulator R they were computed from (phase B, in place; the
+//     MMAs execute in issue order, so G1' q0 of the next iteration rewrites R after GEMM2 q3 has read r);
+//   * the last 64 columns this needs come from y: a quarter of y lives in registers (16 per thread:
+//     the second sub-step of chunks 2 and 3).
+// TMEM columns: y 192 | S 64 | Q 64 | R / r pieces 64 | G0 64 | G1 64 = 512.
 // Barriers (each completes once per iteration of a tile; phase = global iteration counter):
-//   aready[q]  512 arrivals   pieces of chunk q stored             compute -> MMA
-//   sfree[j]   commit         G1' slice j done: slot j & 1 is free for chunk j + 2   MMA -> compute
+//   aready[q]  256 arrivals   pieces of chunk q stored             set q & 1 -> MMA
+//   sfree[j]   commit         G1' slice j done: its slot is free for chunk j + 2   MMA -> set j
 //   rfull      commit         GEMM1 complete                       MMA -> compute
 //   rready     512 arrivals   pieces of r stored                   compute -> MMA
-//   gfull[q]   commit         GEMM2 chunk q complete               MMA -> compute
-//   gfree[j]   512 arrivals   C(j) has G buffer j in registers     compute -> MMA (GEMM2 j + 2)
-// kHist: 0 no stop-test record, 1 hist[it] += sum |z+ - z| (ista.py:93), 2 hist[it] += 1 if any
+//   gfull[q]   commit         GEMM2 chunk q complete               MMA -> set q & 1
+//   gfree[j]   256 arrivals   C(j) has G buffer j in registers     set j -> MMA (GEMM2 j + 2)
+// kHist: 0 no stop-test record, 1 hist[it] += sum |z+ - z| (ista.py:93), 2 hist[it] = 1 if any
 // z+ != z (all a threshold of exactly 0 needs; cheaper than the sum)
 template <int NQ, int kHist>
 __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
@@ -293,13 +301,13 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     mbar_init(&bar_rready, 512);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      mbar_init(&bar_aready[q], 512);
+      mbar_init(&bar_aready[q], 256);
       mbar_init(&bar_gfull[q], 1);
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bar_sfree[j], 1);
-      mbar_init(&bar_gfree[j], 512);
+      mbar_init(&bar_gfree[j], 256);
     }
     fence_mbar_init();
   }
@@ -329,11 +337,21 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     const uint32_t d1_lo = (uint32_t)desc1, d1_hi = (uint32_t)(desc1 >> 32);
     const uint32_t d2_lo = (uint32_t)desc2, d2_hi = (uint32_t)(desc2 >> 32);
     constexpr uint32_t kPiece16 = kPieceBytes >> 4;
+    // descriptor = (hi, base + offset); the add is opaque to the compiler on purpose: left to itself it
+    // hoists ~100 loop-invariant descriptor words out of the iteration loop, spills them, and reloads
+    // them from local memory (~200 cycles) in front of every batch of MMAs, which the tensor pipe,
+    // whose queue is short, then waits for
     auto make64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    auto off = [](uint32_t base, uint32_t o) {
+      uint32_t r;
+      asm volatile("add.u32 %0, %1, %2;" : "=r"(r) : "r"(base), "r"(o));
+      return r;
+    };
     int tr_n = 0;
     bool tr_on = false;
     // slice q of GEMM1 of pass `tg`: R (+)= Y[:, 64 q ...] W^T, three products per k-step
-    // into ONE accumulator (small ones first)
+    // into ONE accumulator (small ones first).  Slice 0 overwrites R, i.e. the pieces of r: it is
+    // issued after the last GEMM2 chunk, and the tensor pipe executes in issue order.
     auto gemm1_slice = [&](int q, uint32_t tg) {
       RES_WAIT(&bar_aready[q], tg);
       RTRACE(11);
@@ -343,8 +361,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t koff = (uint32_t)q * (kSlabBytes >> 4) + (uint32_t)(ks * 2);
-          const uint64_t qh = make64(d1_lo + koff, d1_hi);
-          const uint64_t ql = make64(d1_lo + koff + kPiece16, d1_hi);
+          const uint64_t qh = make64(off(d1_lo, koff), d1_hi);
+          const uint64_t ql = make64(off(d1_lo, koff + kPiece16), d1_hi);
           const uint32_t ah = t_slot + ks * 8, al = ah + 32;
           mma_ts<false>(tbase + kColAccR, ah, ql, idesc1, (q > 0 || ks > 0) ? 1u : 0u);
           mma_ts<false>(tbase + kColAccR, al, qh, idesc1, 1);
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           RTRACE(15);
           if (elect_one()) {
             const uint32_t t_acc = tbase + kColAccG + (uint32_t)(q & 1) * 64u;
-            const uint32_t t_r = tbase + kColQ;
+            const uint32_t t_r = tbase + kColAccR;   // the pieces of r live where R was
             const uint32_t qoff = (uint32_t)q * (kSlabBytes >> 4);
             // small products first (l h', h l'), leading product last
             constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
@@ -390,7 +408,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
               for (int t = 0; t < 3; ++t) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
+                  const uint64_t bd = make64(off(d2_lo, qoff + pb[t] * kPiece16 + ks * 128), d2_hi);
                   mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, (t > 0 || ks > 0) ? 1u : 0u);
                 }
               }
@@ -401,7 +419,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 #pragma unroll
                 for (int ks = 0; ks < 3; ++ks) {
                   if (ks < dsteps) {
-                    const uint64_t bd = make64(d2_lo + qoff + pb[t] * kPiece16 + ks * 128, d2_hi);
+                    const uint64_t bd = make64(off(d2_lo, qoff + pb[t] * kPiece16 + ks * 128), d2_hi);
                     mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
                     acc_on = 1;
                   }
@@ -416,7 +434,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         if (kHist == 1 && it > 0 && lane == 0) {
           // stop-test record of the previous iteration: the compute warps left their partial
           // sums in shared memory before they arrived on bar_rready; ONE atomic per CTA, issued
-          // while the tensor pipe works through the four GEMM2 chunks just queued
+          // while the tensor pipe works through the four GEMM2 chunks just queued.  (Adding them up
+          // with shared-memory float64 atomics on the compute side was measured slower: 62 vs 67 k it/s.)
           double s = 0.0;
 #pragma unroll
           for (int wi = 0; wi < 16; ++wi) s += (double)hist_s[(it - 1) & 1][wi];
@@ -432,8 +451,9 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
   } else if (warp < 16) {
     // ===================== compute warps =====================
     const int quad = warp & 3;                 // TMEM lane quadrant of this warp
-    const int wg = warp >> 2;                  // group 0..3: atoms [16 wg, 16 wg + 16) of every chunk,
-                                               // features [16 wg, 16 wg + 16) in phase B
+    const int wg = warp >> 2;                  // phase B: features [16 wg, 16 wg + 16)
+    const int set = wg >> 1;                   // phase C: set 0 runs chunks 0 and 2, set 1 chunks 1 and 3
+    const int half = wg & 1;                   //          atoms [32 half, 32 half + 32) of the chunk
     const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
     const int ct = tid;                        // 0..511
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -445,34 +465,36 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
     bool tr_on = false;
     bool bad = false;
     uint32_t gi = 0;
-    uint32_t yk[16];                           // chunk 3 of y (NQ = 4): registers, not TMEM
+    uint32_t yk[16];                           // y of the second sub-step of this set's second chunk (NQ = 4)
 #pragma unroll
     for (int j = 0; j < 16; ++j) yk[j] = 0u;
+    const uint32_t t_slot = tbase + lane_base + (set ? kColQ : kColS) + half * 16;   // + 8 s (h), + 32 (l)
+    const uint32_t t_g = tbase + lane_base + kColAccG + set * 64 + half * 32;        // + 16 s
 
-    // 16 values -> fp16 pieces -> this thread's 8 + 8 words of a slot [h 32 cols][l 32 cols]
-    // (even chunks: S, odd chunks: Q); chunk q of the GEMM1 of pass `tg`.  first = the tile's
-    // first pass (pieces of y_0): Q is not in use by a GEMM2 then.
-    auto stage_pieces = [&](const uint32_t (&yv)[16], int q, uint32_t tg, bool first) {
-      uint32_t wh[8], wl[8];
+    // y of (chunk q, sub-step s) lives in registers?  Only with four chunks: 192 columns hold chunks
+    // 0, 1 and the first sub-steps of chunks 2, 3.
+    auto y_in_regs = [](int qi, int s) { return NQ == 4 && qi == 1 && s == 1; };
+    // TMEM column of y of (qi-th chunk of this set, sub-step s)
+    auto y_col = [&](int qi, int s) -> uint32_t {
+      const int q = set + 2 * qi;
+      if (NQ == 4 && qi == 1) return kColY + 128 + set * 32 + half * 16;   // s == 0 only
+      return kColY + q * 64 + half * 32 + s * 16;
+    };
+    // 16 values -> fp16 pieces -> this thread's 8 + 8 words of its set's slot [h 32 cols][l 32 cols]
+    auto split_pieces = [&](const uint32_t (&yv)[16], uint32_t (&wh)[8], uint32_t (&wl)[8]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         split2_pair(make_float2(__uint_as_float(yv[2 * j]), __uint_as_float(yv[2 * j + 1])), wh[j], wl[j]);
-      RTRACE(21);
-      // chunk 0 -> S: free since GEMM1 of the previous pass completed (everybody saw bar_rfull);
-      // chunk 1 -> Q: the last GEMM2 chunk of this iteration must have read the pieces of r;
-      // chunks 2, 3: slice q - 2 of this pass must have consumed the slot
-      if (q == 1 && !first) RES_WAIT(&bar_gfull[NQ - 1], tg - 1u);
-      if (q >= 2) RES_WAIT(&bar_sfree[q - 2], tg);
-      RTRACE(22);
-      const uint32_t t_slot = tbase + lane_base + ((q & 1) ? kColQ : kColS) + wg * 8;
-      tc_fence_after();
-      tmem_st8(t_slot, wh);
-      tmem_st8(t_slot + 32, wl);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&bar_aready[q]);
-      RTRACE(23);
     };
+    auto store_pieces = [&](const uint32_t (&yv)[16], int s) {
+      uint32_t wh[8], wl[8];
+      split_pieces(yv, wh, wl);
+      tmem_st8(t_slot + s * 8, wh);
+      tmem_st8(t_slot + s * 8 + 32, wl);
+    };
+#ifdef LASSO_RES_HOLD
+    uint32_t hold_h[8], hold_l[8];
+#endif
 
     for (int tile = 0; tile < my_tiles; ++tile) {
       const int64_t row0 = (int64_t)(blockIdx.x + (int64_t)tile * gridDim.x) * p.trows;
@@ -484,23 +506,35 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       const float uz_row = sc.sw / row_sx[row];         // code units -> caller units (exact)
       // ---------------- y_0 = z_0 (ista.py:76) and its pieces ----------------
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        uint32_t yv[16];
+      for (int qi = 0; qi < 2; ++qi) {
+        const int q = set + 2 * qi;
+        if (q < NQ) {
+          // the slot of the set's second chunk is free once slice q - 2 of this pass has read it
+          if (qi == 1) RES_WAIT(&bar_sfree[set], gi);
+          tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 z4 = *reinterpret_cast<const float4*>(zs + z_off(row, q * 16 + wg * 4 + j));
-          yv[4 * j + 0] = __float_as_uint(z4.x);
-          yv[4 * j + 1] = __float_as_uint(z4.y);
-          yv[4 * j + 2] = __float_as_uint(z4.z);
-          yv[4 * j + 3] = __float_as_uint(z4.w);
-        }
-        if (q < 3) {
-          tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
-        } else {
+          for (int s = 0; s < 2; ++s) {
+            uint32_t yv[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) yk[j] = yv[j];
+            for (int j = 0; j < 4; ++j) {
+              const float4 z4 = *reinterpret_cast<const float4*>(zs + z_off(row, q * 16 + half * 8 + s * 4 + j));
+              yv[4 * j + 0] = __float_as_uint(z4.x);
+              yv[4 * j + 1] = __float_as_uint(z4.y);
+              yv[4 * j + 2] = __float_as_uint(z4.z);
+              yv[4 * j + 3] = __float_as_uint(z4.w);
+            }
+            if (y_in_regs(qi, s)) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) yk[j] = yv[j];
+            } else {
+              tmem_st16(tbase + lane_base + y_col(qi, s), yv);
+            }
+            store_pieces(yv, s);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_aready[q]);
         }
-        stage_pieces(yv, q, gi, true);
       }
 
       float beta_next = __ldg(p.beta);         // fetched one iteration ahead: a global load costs ~600 cycles
@@ -509,7 +543,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         const bool more = it + 1 < iters;      // pieces are only needed if another GEMM1 follows
         const float2 beta2 = make_float2(beta_next, beta_next);
         if (more) beta_next = __ldg(p.beta + it + 1);
-        // ---------------- phase B: r = R - x -> pieces (16 features per thread) -> Q ----------------
+        // ---------------- phase B: r = R - x -> pieces, in place (16 features per thread) ----------------
         {
           float4 xv[4];
 #pragma unroll
@@ -530,7 +564,9 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
             split2_pair(ra, wh[2 * j], wl[2 * j]);
             split2_pair(rc, wh[2 * j + 1], wl[2 * j + 1]);
           }
-          const uint32_t t_r = tbase + lane_base + kColQ + wg * 8;
+          // the pieces go where R was: every warp of the tile must have its part of R in registers
+          compute_sync();
+          const uint32_t t_r = tbase + lane_base + kColAccR + wg * 8;
           tmem_st8(t_r, wh);
           tmem_st8(t_r + 32, wl);
           tmem_wait_st();
@@ -540,64 +576,125 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         }
         // ---------------- phase C (+ pieces of the next iteration) ----------------
         float part = 0.f, part_b = 0.f;   // two chains: 64 dependent adds per iteration otherwise
-        uint32_t any = 0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          // y does not depend on the MMAs: its load is in flight while this thread waits for G
-          uint32_t g[16], yv[16];
-          if (q < 3) {
-            tmem_ld16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) yv[j] = yk[j];
-          }
-          RES_WAIT(&bar_gfull[q], gi);
-          RTRACE(40);
-          tc_fence_after();
-          tmem_ld16(tbase + lane_base + kColAccG + (q & 1) * 64 + wg * 16, g);
-          tmem_wait_ld();
-          if (q + 2 < NQ) {
-            tc_fence_before();
-            mbar_arrive(&bar_gfree[q]);   // accumulator is in registers: hand the buffer to chunk q + 2
-          }
-          RTRACE(42);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint8_t* zp = zs + z_off(row, q * 16 + wg * 4 + j);
-            float4 z4 = *reinterpret_cast<const float4*>(zp);
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const float2 yy = make_float2(__uint_as_float(yv[4 * j + 2 * h2]), __uint_as_float(yv[4 * j + 2 * h2 + 1]));
-              const float2 gg = make_float2(__uint_as_float(g[4 * j + 2 * h2]), __uint_as_float(g[4 * j + 2 * h2 + 1]));
-              const float2 zz = h2 ? make_float2(z4.z, z4.w) : make_float2(z4.x, z4.y);
-              // softshrink(y - lr g, lam) (ista.py:90): v - clamp(v, +-lam) is bit-identical to the
-              // three-way select; the step itself is one fused multiply-add
-              const float2 v = __ffma2_rn(nlr2, gg, yy);
-              const float2 c = make_float2(fminf(fmaxf(v.x, -lam), lam), fminf(fmaxf(v.y, -lam), lam));
-              const float2 zn = rsub2(v, c);
-              const float2 dl = rsub2(zn, zz);                       // z+ - z
-              if (kHist == 1) {                                      // stop-test sum (ista.py:93)
-                if (h2) part_b += fabsf(dl.x) + fabsf(dl.y);
-                else part += fabsf(dl.x) + fabsf(dl.y);
-              }
-              if (kHist == 2) any |= __float_as_uint(dl.x) | __float_as_uint(dl.y);
-              const float2 yn = __ffma2_rn(beta2, dl, zn);           // ista.py:100
-              if (h2) { z4.z = zn.x; z4.w = zn.y; }
-              else { z4.x = zn.x; z4.y = zn.y; }
-              yv[4 * j + 2 * h2] = __float_as_uint(yn.x);
-              yv[4 * j + 2 * h2 + 1] = __float_as_uint(yn.y);
+        for (int qi = 0; qi < 2; ++qi) {
+          const int q = set + 2 * qi;
+          if (q < NQ) {
+#ifdef LASSO_RES_EARLY_DRAIN
+            // both halves of this thread's part of G leave the buffer at once, so that GEMM2 q + 2 can
+            // start ~600 cycles earlier (costs 16 live registers during the first sub-step)
+            uint32_t g2[2][16];
+            RES_WAIT(&bar_gfull[q], gi);
+            RTRACE(40);
+            tc_fence_after();
+            tmem_ld16(t_g, g2[0]);
+            tmem_ld16(t_g + 16, g2[1]);
+            tmem_wait_ld();
+            if (q + 2 < NQ) {
+              tc_fence_before();
+              mbar_arrive(&bar_gfree[set]);
             }
-            *reinterpret_cast<float4*>(zp) = z4;
-          }
-          if (q < 3) {
-            tmem_st16(tbase + lane_base + kColY + q * 64 + wg * 16, yv);
-          } else {
+#endif
 #pragma unroll
-            for (int j = 0; j < 16; ++j) yk[j] = yv[j];
+            for (int s = 0; s < 2; ++s) {
+              // y does not depend on the MMAs: its load is in flight while this thread waits for G
+              uint32_t yv[16];
+              if (y_in_regs(qi, s)) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yv[j] = yk[j];
+              } else {
+                tmem_ld16(tbase + lane_base + y_col(qi, s), yv);
+              }
+#ifdef LASSO_RES_EARLY_DRAIN
+              uint32_t (&g)[16] = g2[s];
+              if (!y_in_regs(qi, s)) tmem_wait_ld();
+#else
+              uint32_t g[16];
+              if (s == 0) {
+                RES_WAIT(&bar_gfull[q], gi);
+                RTRACE(40);
+                tc_fence_after();
+              }
+              tmem_ld16(t_g + s * 16, g);
+              tmem_wait_ld();
+              if (s == 1 && q + 2 < NQ) {
+                tc_fence_before();
+                mbar_arrive(&bar_gfree[set]);   // accumulator is in registers: hand the buffer to chunk q + 2
+              }
+#endif
+              RTRACE(42);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint8_t* zp = zs + z_off(row, q * 16 + half * 8 + s * 4 + j);
+                float4 z4 = *reinterpret_cast<const float4*>(zp);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const float2 yy = make_float2(__uint_as_float(yv[4 * j + 2 * h2]), __uint_as_float(yv[4 * j + 2 * h2 + 1]));
+                  const float2 gg = make_float2(__uint_as_float(g[4 * j + 2 * h2]), __uint_as_float(g[4 * j + 2 * h2 + 1]));
+                  const float2 zz = h2 ? make_float2(z4.z, z4.w) : make_float2(z4.x, z4.y);
+                  // softshrink(y - lr g, lam) (ista.py:90): v - clamp(v, +-lam) is bit-identical to the
+                  // three-way select; the step itself is one fused multiply-add
+                  const float2 v = __ffma2_rn(nlr2, gg, yy);
+                  const float2 c = make_float2(fminf(fmaxf(v.x, -lam), lam), fminf(fmaxf(v.y, -lam), lam));
+                  const float2 zn = rsub2(v, c);
+                  const float2 dl = rsub2(zn, zz);                       // z+ - z
+                  if (kHist != 0) {                                      // stop-test sum (ista.py:93)
+                    // (mode 2 only asks whether the sum is non-zero; it takes the same adds, which run
+                    // on the FMA pipe, rather than OR-ing the bit patterns on the busier ALU pipe)
+                    if (h2) part_b += fabsf(dl.x) + fabsf(dl.y);
+                    else part += fabsf(dl.x) + fabsf(dl.y);
+                  }
+                  const float2 yn = __ffma2_rn(beta2, dl, zn);           // ista.py:100
+                  if (h2) { z4.z = zn.x; z4.w = zn.y; }
+                  else { z4.x = zn.x; z4.y = zn.y; }
+                  yv[4 * j + 2 * h2] = __float_as_uint(yn.x);
+                  yv[4 * j + 2 * h2 + 1] = __float_as_uint(yn.y);
+                }
+                *reinterpret_cast<float4*>(zp) = z4;
+              }
+              if (y_in_regs(qi, s)) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yk[j] = yv[j];
+              } else {
+                tmem_st16(tbase + lane_base + y_col(qi, s), yv);
+              }
+              RTRACE(41);
+              if (more) {
+                // The set's first chunk finds its slot free (GEMM1 of the previous pass completed:
+                // everybody saw bar_rfull).  The second one has to wait for slice q - 2 of this pass,
+                // which the tensor pipe reaches only after the last GEMM2 chunk: its first sub-step
+                // keeps its pieces in registers (LASSO_RES_HOLD) or re-reads y+ from TMEM afterwards
+                // instead of stalling in the middle of the chunk.
+                if (qi == 0) {
+                  store_pieces(yv, s);
+                } else if (s == 0) {
+#ifdef LASSO_RES_HOLD
+                  split_pieces(yv, hold_h, hold_l);
+#endif
+                } else {
+                  RES_WAIT(&bar_sfree[set], gi + 1u);
+                  tc_fence_after();
+                  RTRACE(22);
+                  store_pieces(yv, 1);
+#ifdef LASSO_RES_HOLD
+                  tmem_st8(t_slot, hold_h);
+                  tmem_st8(t_slot + 32, hold_l);
+#else
+                  tmem_wait_st();          // y+ of sub-step 0 is in TMEM (never the register-resident part)
+                  tmem_ld16(tbase + lane_base + y_col(1, 0), yv);
+                  tmem_wait_ld();
+                  store_pieces(yv, 0);
+#endif
+                }
+              }
+            }
+            tmem_wait_st();            // pieces and y
+            if (more) {
+              tc_fence_before();
+              mbar_arrive(&bar_aready[q]);
+              RTRACE(23);
+            }
           }
-          RTRACE(41);
-          if (more) stage_pieces(yv, q, gi + 1, false);   // its wait::st also covers the y store
-          else if (q < 3) tmem_wait_st();
         }
         if (kHist != 0) {
           float s;
@@ -606,7 +703,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
           } else {
-            s = __any_sync(0xffffffffu, (any & 0x7FFFFFFFu) != 0u) ? 1.f : 0.f;
+            s = __any_sync(0xffffffffu, part + part_b > 0.f) ? 1.f : 0.f;
           }
           if (lane == 0) {
             if (kHist == 2) {

@@ -54,6 +54,20 @@ def _worker(rank, world, port, out_dir):
                                   device="cpu", progbar=False, group=group, algorithm="ista",
                                   maxiter=int(gd["maxiter"]))
         res["w"], res["losses"] = w, losses
+        # (4) the same with the step pinned (bit-reproducible reference => tight bound) and a tolerance
+        # that makes the GLOBAL stop test fire early in some EM steps (the redo path of the packed step)
+        for key, name, tol in (("pin", "r2_dict_learning_pinned_constrained", 1e-5),
+                               ("pin_ridge", "r2_dict_learning_pinned_ridge", 1e-5)):
+            gp = load_golden(name)
+            rows = slice(rank * nd // world, (rank + 1) * nd // world)
+            torch.manual_seed(0)
+            res[key] = dict_learning(gp["x"][rows], 50, alpha=gp["alpha"], constrained=key == "pin",
+                                     steps=int(gp["steps"]), lambd=gp["lambd"], device="cpu", progbar=False,
+                                     group=group, algorithm="ista", maxiter=int(gp["maxiter"]), lr=gp["lr"],
+                                     tol=tol)
+        torch.manual_seed(0)
+        res["early"] = dict_learning(gd["x"][rows], 50, alpha=gd["alpha"], steps=4, device="cpu",
+                                     progbar=False, group=group, maxiter=300, lr=0.05, tol=1e-3)
         torch.save(res, os.path.join(out_dir, "r%d.pt" % rank))
     finally:
         dist.destroy_process_group()
@@ -74,3 +88,14 @@ def test_sharded_encode_and_dict_learning(tmp_path):
     assert torch.equal(parts[0]["w"], parts[1]["w"])         # replicated without a broadcast
     assert torch.allclose(parts[0]["losses"], gd["losses"], rtol=2e-4)
     assert rel_fro(parts[0]["w"], gd["weight"]) <= 5e-3
+    for key, name in (("pin", "r2_dict_learning_pinned_constrained"), ("pin_ridge", "r2_dict_learning_pinned_ridge")):
+        gp = load_golden(name)
+        w, losses = parts[0][key]
+        assert torch.equal(w, parts[1][key][0])
+        assert torch.allclose(losses, gp["losses"], rtol=1e-6) and rel_fro(w, gp["weight"]) <= 1e-5
+    # early global stop inside sharded EM steps: equals the unsharded oracle run with the same options
+    torch.manual_seed(0)
+    want_w, want_losses = oracle.dict_learning(gd["x"], 50, alpha=gd["alpha"], steps=4, maxiter=300, lr=0.05, tol=1e-3)
+    w, losses = parts[0]["early"]
+    assert torch.equal(w, parts[1]["early"][0])
+    assert torch.allclose(losses, want_losses, rtol=1e-5) and rel_fro(w, want_w) <= 1e-4

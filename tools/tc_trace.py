@@ -21,10 +21,14 @@ names = {1: "P:empty_ok", 10: "M:tile", 11: "M:aready_ok", 12: "M:commit_chunk",
          15: "M:gfree_ok", 16: "M:commit_g", 20: "C:full_ok", 21: "C:math_done", 22: "C:sfree_ok", 23: "C:st_done",
          30: "C:rfull_ok", 31: "C:phaseB_done", 40: "C:gfull_ok", 41: "C:epi_done", 50: "C:tile_end"}
 if kpath == "resident":
-    names = {10: "M:acc_free", 11: "M:aready_ok", 12: "M:commit_chunk", 14: "M:rready_ok", 15: "M:gfree_ok",
-             16: "M:commit_g", 20: "A:y_loaded", 21: "A:split_done", 22: "A:stage_free", 23: "A:arrived",
+    # MMA warp: 18 iteration top, 14 r pieces ready, 15 G buffer free (before a GEMM2 chunk is issued), 16 GEMM2
+    # chunk committed, 11 pieces of a chunk ready, 12 GEMM1 slice committed.  Compute warps (0 / 4: set A, 8 / 12:
+    # set B): 30 R complete, 31 phase B done, 40 G of the chunk complete, 42 sub-step's G in registers, 41 sub-step's
+    # arithmetic done, 22 piece slot free, 23 pieces stored and signalled
+    names = {11: "M:aready_ok", 12: "M:commit_chunk", 14: "M:rready_ok", 15: "M:gfree_ok",
+             16: "M:commit_g", 22: "A:stage_free", 23: "A:arrived",
              30: "B:rfull_ok", 31: "B:done", 40: "C:gfull_ok", 41: "C:chunk_done", 42: "C:gfree_arrived",
-             17: "M:gfree0_ok", 18: "M:iter_top"}
+             18: "M:iter_top"}
 for wi in [int(v) for v in os.environ.get("TRACE_WARPS", "0,2,4,12" if kpath != "resident" else "16,0,4,8,12").split(",")]:
     print("---- warp", wi)
     prev = None
