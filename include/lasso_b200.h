@@ -150,6 +150,44 @@ int32_t lasso_b200_lipschitz_f32(const float* weight, int32_t d, int32_t k,
                                  int32_t iters, double* l_out, void* stream);
 
 /*
+ * Exact Lipschitz constant of the convolutional dictionary: lambda_max of conv2d^T conv2d on images
+ * of size [cin, h, w] -- replaces lip_constant, lasso/conv2d/lip_const.py:8-31 (ARPACK eigsh on a host
+ * LinearOperator with one conv2d + conv_transpose2d + D2H/H2D per step).  The operator is formed
+ * densely in image space (cin*h*w <= 4096) from the tap Gram of the filters and goes through the same
+ * lambda_max kernels as lasso_b200_lipschitz_f32.  Any kernel size / stride / padding (the reference's
+ * fast bound, lip_const.py:96-135, takes odd kernels and stride 1 only).
+ *   weight   device [filters, cin, kh, kw] float32      iters   cap on the power steps (2000 is plenty)
+ *   l_out    HOST double.  Synchronises the stream.
+ */
+int32_t lasso_b200_conv2d_lipschitz_f32(const float* weight, int32_t filters, int32_t cin, int32_t kh,
+                                        int32_t kw, int32_t h, int32_t w, int32_t stride,
+                                        int32_t padding, int32_t iters, double* l_out, void* stream);
+
+/*
+ * Ridge warm start  z_out = ((W^T W + alpha I)^-1 W^T x^T)^T  -- initialize_code(mode='ridge'),
+ * sparse_encode.py:28-29 -> ridge, utils.py:28-40 (k x k Gram, float32 Cholesky, n right-hand sides).
+ * Computed as ONE [n,d] x [d,k] product z_out = x T with T = (W W^T + alpha I)^-1 W = W (W^T W +
+ * alpha I)^-1 taken from the smaller of the two systems (float64 Gram, one-CTA blocked Cholesky --
+ * float64 for min(d,k) <= 64, float32 beyond, like the reference's own factorisation -- and one warp per
+ * right-hand side); min(d,k) <= 320.
+ *   x, weight   device, read-only          z_out   device [n,k]
+ *   not_positive_definite   HOST int32: set to 1 when the regularised Gram has a non-positive
+ *                           pivot -- the caller raises the reference's RuntimeError (utils.py:35-38)
+ * Synchronises the stream (the reference reads `info` back at the same point).
+ */
+int32_t lasso_b200_ridge_init_f32(const float* x, const float* weight, int64_t n, int32_t d, int32_t k,
+                                  double alpha, float* z_out, int32_t* not_positive_definite,
+                                  void* stream);
+
+/*
+ * z_out[n,k] = x[n,d] t[d,k], float32 (FFMA, fp32 accumulate): initialize_code(mode='transpose'),
+ * sparse_encode.py:30-31 (`torch.matmul(x, weight)`), and the n-sized step of the ridge start when its
+ * small system is solved by the caller.  All pointers device; asynchronous.
+ */
+int32_t lasso_b200_matmul_f32(const float* x, const float* t, int64_t n, int32_t d, int32_t k,
+                              float* z_out, void* stream);
+
+/*
  * Loss terms of lasso_loss, dict_learning.py:10-13:
  *   out[0] = sum (x - z weight^T)^2      out[1] = sum |z|
  * out: DEVICE pointer to 2 doubles (overwritten).  The caller forms

@@ -29,6 +29,9 @@ EXPORTS = (
     "lasso_b200_fista_f32_host",
     "lasso_b200_conv2d_fista_f32",
     "lasso_b200_lipschitz_f32",
+    "lasso_b200_conv2d_lipschitz_f32",
+    "lasso_b200_ridge_init_f32",
+    "lasso_b200_matmul_f32",
     "lasso_b200_loss_terms_f32",
     "lasso_b200_gram_f32",
     "lasso_b200_dict_update_gram_f32",
@@ -72,6 +75,13 @@ def _declare(lib):
                                                 f64, f64, i32, i32, f64, c.POINTER(i32), vp, vp]
     lib.lasso_b200_lipschitz_f32.restype = i32
     lib.lasso_b200_lipschitz_f32.argtypes = [vp, i32, i32, i32, c.POINTER(f64), vp]
+    lib.lasso_b200_conv2d_lipschitz_f32.restype = i32
+    lib.lasso_b200_conv2d_lipschitz_f32.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                                    c.POINTER(f64), vp]
+    lib.lasso_b200_ridge_init_f32.restype = i32
+    lib.lasso_b200_ridge_init_f32.argtypes = [vp, vp, i64, i32, i32, f64, vp, c.POINTER(i32), vp]
+    lib.lasso_b200_matmul_f32.restype = i32
+    lib.lasso_b200_matmul_f32.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     lib.lasso_b200_loss_terms_f32.restype = i32
     lib.lasso_b200_loss_terms_f32.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     lib.lasso_b200_gram_f32.restype = i32
@@ -245,6 +255,51 @@ def _f64_out(t, numel, name):
     if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == numel):
         raise ValueError("{} must be a contiguous float64 CUDA tensor of {} elements".format(name, numel))
     return t
+
+
+def conv2d_lipschitz(weight, imsize, stride=1, padding=0, iters=2000) -> float:
+    """lambda_max of conv2d^T conv2d on [cin, h, w] images (dense operator + the dictionary's eigen-solver)."""
+    lib = load()
+    weight = _dev_f32(weight, "weight")
+    filters, cin, kh, kw = weight.shape
+    h, w = imsize
+    out = ctypes.c_double(0.0)
+    with torch.cuda.device(weight.device):
+        _check(lib.lasso_b200_conv2d_lipschitz_f32(
+            weight.data_ptr(), filters, cin, kh, kw, int(h), int(w), int(stride), int(padding), int(iters),
+            ctypes.byref(out), _stream_ptr(weight.device)))
+    return out.value
+
+
+def ridge_init(x, weight, alpha):
+    """z0[n,k] = ((W^T W + alpha I)^-1 W^T x^T)^T on the device; RuntimeError if the Gram is not PD."""
+    lib = load()
+    x, weight = _dev_f32(x, "x"), _dev_f32(weight, "weight")
+    n, d = x.shape
+    k = weight.shape[1]
+    z = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    flag = ctypes.c_int32(0)
+    with torch.cuda.device(x.device):
+        _check(lib.lasso_b200_ridge_init_f32(x.data_ptr(), weight.data_ptr(), n, d, k, float(alpha),
+                                             z.data_ptr(), ctypes.byref(flag), _stream_ptr(x.device)))
+    if flag.value:
+        raise RuntimeError("The Gram matrix is not positive definite. "
+                           "Try increasing 'alpha'.")          # utils.py:36-38
+    return z
+
+
+def matmul(x, t):
+    """x[n,d] @ t[d,k] in float32 on the library's FFMA kernel."""
+    lib = load()
+    x, t = _dev_f32(x, "x"), _dev_f32(t, "t")
+    n, d = x.shape
+    k = t.shape[1]
+    if t.shape[0] != d:
+        raise LassoB200Error("t must be [d,k] with d == x.shape[1]")
+    z = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.lasso_b200_matmul_f32(x.data_ptr(), t.data_ptr(), n, d, k, z.data_ptr(), _stream_ptr(x.device)))
+    return z
 
 
 def loss_terms(x, z, weight, out=None) -> torch.Tensor:

@@ -7,6 +7,10 @@ im2col -> linear on the k-blocked tcgen05 kernel (``lasso_b200_conv2d_fista_f32`
 iteration.  Codes keep the reference's layout ``[n, filters, oh, ow]`` at the boundary; inside
 they are patch-major rows ``[n*oh*ow, filters]`` (two permutes per call).
 
+``lr='exact'`` (an extension) takes the step from the exact Lipschitz constant of the convolutional
+dictionary (power iteration on the device, any kernel size / stride / padding); ``lr='auto'`` keeps the
+reference's Fourier bound and its restrictions (odd kernels, stride 1).
+
 Built: any integer ``stride`` / ``padding`` (the same for both axes), ``cin*kh*kw <= 128``,
 ``filters <= 1024`` (multiples of 4), one image's patch matrix within 200 KB of shared memory.
 Everything else raises -- there is no PyTorch fallback.
@@ -18,13 +22,20 @@ import torch
 
 from .. import _cabi
 from ..linear import utils as _utils
-from .lip_const import lip_bound_conv2d
+from .lip_const import lip_bound_conv2d, lip_constant
 
 __all__ = ["ista_conv2d"]
 
 
 def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
                 maxiter=10, lr='auto', tol=1e-5, verbose=False):
+    if lr == 'exact':
+        # Extension (the reference has no such option): the exact constant lambda_max(conv2d^T conv2d) for
+        # this image size, computed on the device -- any kernel size / stride / padding, e.g. BASELINE
+        # config 5's 8x8 filters, for which lr='auto' raises in the reference (lip_const.py:101-102).
+        # The value is a Rayleigh quotient (never above the eigenvalue, ~1e-5 below at worst when the top
+        # of the spectrum is a cluster), hence the 1e-4 margin on the step.
+        lr = 1 / (1.0001 * lip_constant(weight, x.shape[-2:], stride=stride, padding=padding))
     if lr == 'auto':
         if stride != 1:
             raise NotImplementedError("auto lr is only implemented for "

@@ -8,7 +8,32 @@ import math
 
 import torch
 
-__all__ = ["lip_bound_conv2d"]
+from .. import _cabi
+from ..linear import utils as _utils
+
+__all__ = ["lip_bound_conv2d", "lip_constant"]
+
+
+@torch.no_grad()
+def lip_constant(kernel, imsize, transpose=False, sqrt=False, stride=1, padding=0):
+    """Largest eigenvalue of conv2d^T conv2d (``transpose=False``) / conv2d conv2d^T (``True``) on images
+    of ``imsize`` -- the reference's ``lip_constant`` (lasso/conv2d/lip_const.py:8-31: ARPACK ``eigsh`` on a
+    host ``LinearOperator``, a conv2d + conv_transpose2d + two host copies per Lanczos step) on the device
+    (``lasso_b200_conv2d_lipschitz_f32``: the operator formed densely in image space, then the eigen-solver
+    of the dictionary's Lipschitz constant).  Any kernel size, stride and padding (``stride`` / ``padding``
+    are the reference's ``**kwargs``); ``cin*h*w <= 4096``.  Both operators share their non-zero spectrum, so
+    ``transpose`` only says which side ``imsize`` describes: the image (False) or the code grid (True)."""
+    if not (isinstance(stride, int) and isinstance(padding, int)):
+        raise NotImplementedError("one integer stride / padding for both axes")
+    out_channels, in_channels, kh, kw = kernel.shape
+    height, width = imsize
+    if transpose:       # imsize is the code grid: the image it decodes to
+        height = (height - 1) * stride - 2 * padding + kh
+        width = (width - 1) * stride - 2 * padding + kw
+    dev = kernel.device if kernel.is_cuda else _utils.default_device()
+    eig = _cabi.conv2d_lipschitz(kernel.detach().to(dev).contiguous(), (height, width), stride=stride,
+                                 padding=padding)
+    return math.sqrt(eig) if sqrt else eig
 
 
 def lip_bound_conv2d(kernel, padding, stride=1, sample=50, sqrt=False):

@@ -677,6 +677,12 @@ __global__ void zero_columns_kernel(float* __restrict__ z, int64_t n, int k, con
 
 }  // namespace
 
+void small_gram_launch(const float* w, int d, int k, int m, int len, int row_gram, double* gram, cudaStream_t st) {
+  dim3 grid((m + 15) / 16, (m + 15) / 16), block(16, 16);
+  small_gram_kernel<<<grid, block, 0, st>>>(w, d, k, m, len, row_gram, gram);
+  count_launch();
+}
+
 int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t st) {
   if (n == 0) return LASSO_B200_OK;
   const int64_t total = n * (int64_t)k;
@@ -687,16 +693,9 @@ int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t s
   return LASSO_B200_OK;
 }
 
-int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
-                  cudaStream_t st) {
-  // scratch (doubles): [m*m] Gram | [2*m] spare | [8] result | then floats: 2 x [m*m] powers of the Gram, [8] traces
-  const int row_gram = d <= k ? 1 : 0;
-  const int m = row_gram ? d : k;
-  const int len = row_gram ? k : d;
-  dim3 grid((m + 15) / 16, (m + 15) / 16), block(16, 16);
-  small_gram_kernel<<<grid, block, 0, st>>>(w, d, k, m, len, row_gram, scratch);
-  LASSO_CHECK_LAUNCH();
-  count_launch();
+// lambda_max of a symmetric PSD m x m matrix already in scratch[0 .. m*m) (float64); scratch layout as in
+// lipschitz_run.  Shared by the dictionary's Lipschitz constant and the convolutional one (conv_lip.cu).
+int lambda_max_run(double* scratch, int m, int iters, double* l_dev, cudaStream_t st) {
   if (m <= 64) power_iter_small_kernel<<<1, 64, 0, st>>>(scratch, m, iters, l_dev);
   else {
     // float region behind the doubles: two m x m ping-pong matrices + 8 traces
@@ -716,6 +715,24 @@ int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double
   LASSO_CHECK_LAUNCH();
   count_launch();
   return LASSO_B200_OK;
+}
+
+// doubles needed by lambda_max_run for an m x m matrix (incl. the result slot behind the Gram)
+size_t lambda_max_scratch_doubles(int m) {
+  return (size_t)m * m + 2 * (size_t)m + 8 + ((2 * (size_t)m * m + 8) * sizeof(float) + 7) / 8;
+}
+
+int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
+                  cudaStream_t st) {
+  // scratch (doubles): [m*m] Gram | [2*m] spare | [8] result | then floats: 2 x [m*m] powers of the Gram, [8] traces
+  const int row_gram = d <= k ? 1 : 0;
+  const int m = row_gram ? d : k;
+  const int len = row_gram ? k : d;
+  dim3 grid((m + 15) / 16, (m + 15) / 16), block(16, 16);
+  small_gram_kernel<<<grid, block, 0, st>>>(w, d, k, m, len, row_gram, scratch);
+  LASSO_CHECK_LAUNCH();
+  count_launch();
+  return lambda_max_run(scratch, m, iters, l_dev, st);
 }
 
 int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz, double* gzx,

@@ -734,6 +734,55 @@ int32_t lasso_b200_lipschitz_f32(const float* weight, int32_t d, int32_t k, int3
   return LASSO_B200_OK;
 }
 
+int32_t lasso_b200_conv2d_lipschitz_f32(const float* weight, int32_t filters, int32_t cin, int32_t kh,
+                                        int32_t kw, int32_t h, int32_t w, int32_t stride, int32_t padding,
+                                        int32_t iters, double* l_out, void* stream) {
+  t_error[0] = 0;
+  if (!weight || !l_out || filters <= 0 || cin <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || padding < 0 ||
+      h + 2 * padding < kh || w + 2 * padding < kw || iters <= 0) {
+    set_error("invalid argument to conv2d_lipschitz");
+    return LASSO_B200_ERR_INVALID;
+  }
+  if ((int64_t)cin * h * w > 4096) {
+    set_error("conv2d_lipschitz: cin*h*w = %lld exceeds 4096 (dense operator)", (long long)cin * h * w);
+    return LASSO_B200_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Lease ws;
+  int rc = ws.acquire(st);
+  if (rc) return rc;
+  if ((rc = ensure(ws->scratch, conv_lipschitz_scratch_bytes(cin, kh, kw, h, w)))) return rc;
+  return conv_lipschitz_run(weight, filters, cin, kh, kw, h, w, stride, padding, iters, l_out,
+                            ws->scratch.ptr, st);
+}
+
+int32_t lasso_b200_ridge_init_f32(const float* x, const float* weight, int64_t n, int32_t d, int32_t k,
+                                  double alpha, float* z_out, int32_t* not_positive_definite, void* stream) {
+  t_error[0] = 0;
+  int rc = check_problem(x, weight, z_out, n, d, k);
+  if (rc) return rc;
+  if (!not_positive_definite || !std::isfinite(alpha)) {
+    set_error("invalid argument to ridge_init");
+    return LASSO_B200_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Lease ws;
+  if ((rc = ws.acquire(st))) return rc;
+  if ((rc = ensure(ws->scratch, ridge_scratch_bytes(d, k)))) return rc;
+  int flag = 0;
+  rc = ridge_init_run(x, weight, n, d, k, alpha, z_out, ws->scratch.ptr, &flag, st);
+  *not_positive_definite = flag;
+  return rc;
+}
+
+int32_t lasso_b200_matmul_f32(const float* x, const float* t, int64_t n, int32_t d, int32_t k, float* z_out,
+                              void* stream) {
+  t_error[0] = 0;
+  int rc = check_problem(x, t, z_out, n, d, k);
+  if (rc) return rc;
+  return matmul_run(x, t, n, d, k, z_out, (cudaStream_t)stream);
+}
+
 int32_t lasso_b200_loss_terms_f32(const float* x, const float* z, const float* weight, int64_t n,
                                   int32_t d, int32_t k, double* out, void* stream) {
   t_error[0] = 0;

@@ -137,6 +137,15 @@ int fista_tc_run(const FistaArgs& a, float* z_out, cudaStream_t st);
 
 int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
                   cudaStream_t st);
+int lambda_max_run(double* scratch, int m, int iters, double* l_dev, cudaStream_t st);
+size_t lambda_max_scratch_doubles(int m);
+size_t conv_lipschitz_scratch_bytes(int cin, int kh, int kw, int h, int w);
+int conv_lipschitz_run(const float* weight, int f, int cin, int kh, int kw, int h, int w, int stride,
+                       int pad, int iters, double* l_out, void* scratch, cudaStream_t st);
+int matmul_run(const float* x, const float* t, int64_t n, int d, int k, float* z, cudaStream_t st);
+size_t ridge_scratch_bytes(int d, int k);
+int ridge_init_run(const float* x, const float* w, int64_t n, int d, int k, double alpha, float* z_out,
+                   void* scratch, int* not_pd, cudaStream_t st);
 int loss_terms_run(const float* x, const float* z, const float* w, int64_t n, int d, int k,
                    double* out, cudaStream_t st);
 int gradient_run(const float* x, const float* point, const float* w, int64_t n, int d, int k,

@@ -1,7 +1,8 @@
 """Small dense helpers on the sparse_encode boundary (mirrors lasso/linear/utils.py).
 
-Only ``ridge`` is reachable from the ISTA path (``init='ridge'``,
-sparse_encode.py:28-29); it works on k x k systems and stays in torch.
+``init='ridge'`` (sparse_encode.py:28-29) runs in the library (``lasso_b200_ridge_init_f32``); the
+generic ``ridge`` / ``lstsq`` helpers below mirror lasso/linear/utils.py for callers that used them
+directly and stay in torch.
 """
 from __future__ import annotations
 

@@ -734,3 +734,78 @@ def test_integration_stub_runs_as_written(dev):
     z = ns["ista"](g["x"].to(dev), g["z0"].to(dev), g["weight"].to(dev), alpha=g["alpha"], lr='auto',
                    maxiter=int(g["maxiter"]), tol=g["tol"])
     assert rel_fro(z, g["z"]) <= 5e-5       # lr='auto': the reference's own ARPACK value wobbles ~1e-6
+
+
+def _conv_operator_lambda_max(w, imsize, stride, padding):
+    """float64 dense reference: the matrix of conv2d on [cin, h, w] images, then eigvalsh of A^T A."""
+    import torch.nn.functional as F
+    cin, (h, wd) = w.shape[1], imsize
+    eye = torch.eye(cin * h * wd, dtype=torch.float64).reshape(-1, cin, h, wd)
+    cols = F.conv2d(eye, w.double(), stride=stride, padding=padding).flatten(1)      # row i = A e_i
+    return float(torch.linalg.eigvalsh(cols @ cols.T)[-1])
+
+
+@pytest.mark.parametrize("filters,cin,ks,size,stride,padding", [
+    (16, 1, 8, 20, 1, 0), (12, 4, 3, 12, 1, 1), (16, 4, 4, 20, 2, 1), (8, 2, 5, 9, 1, 0)])
+def test_conv2d_exact_lipschitz_constant(dev, filters, cin, ks, size, stride, padding):
+    """lip_constant (lip_const.py:8-31) as a device power iteration, against the dense operator in float64."""
+    from lasso_b200.conv2d import lip_constant
+    g = torch.Generator().manual_seed(filters + ks)
+    w = torch.randn(filters, cin, ks, ks, generator=g)
+    w = w / w.flatten(1).norm(dim=1).view(-1, 1, 1, 1)
+    want = _conv_operator_lambda_max(w, (size, size), stride, padding)
+    got = lip_constant(w.to(dev), (size, size), stride=stride, padding=padding)
+    # a Rayleigh quotient: never above the eigenvalue; the top of a convolution's spectrum is a cluster, so
+    # the eigenvector (float32) is the limit: ~1e-5 relative at worst
+    assert want * (1 - 1e-4) <= got <= want * (1 + 1e-9)
+    o = (size + 2 * padding - ks) // stride + 1
+    got_t = lip_constant(w, (o, o), transpose=True, stride=stride, padding=padding, sqrt=True)   # CPU tensor in
+    assert abs(got_t ** 2 - want) <= 1e-4 * want
+
+
+def test_conv2d_lr_exact_for_even_kernels(dev):
+    """lr='exact': config 5's 8x8 filters get an automatic step (lr='auto' raises for even kernels, like the
+    reference: lip_const.py:101-102); the solve equals the oracle run with the same step."""
+    from lasso_b200.conv2d import ista_conv2d, lip_constant
+    g = load_golden("conv_8x8_fista")
+    xd, wd, z0 = g["x"].to(dev), g["weight"].to(dev), g["z0"].to(dev)
+    with pytest.raises(ValueError):
+        ista_conv2d(xd, z0, wd, alpha=g["alpha"], lr='auto', maxiter=3)
+    lr = 1 / (1.0001 * lip_constant(wd, xd.shape[-2:]))
+    z = ista_conv2d(xd, z0, wd, alpha=g["alpha"], lr='exact', maxiter=15, tol=0.0)
+    want = oracle.conv2d_ista(g["x"], g["z0"], g["weight"], alpha=g["alpha"], fast=True, maxiter=15, lr=lr, tol=0.0)
+    assert rel_fro(z, want) <= TOL
+    # the exact constant is what makes the step safe: the objective decreases monotonically under plain ISTA
+    losses = []
+    for it in (1, 5, 20):
+        zi = ista_conv2d(xd, z0, wd, alpha=g["alpha"], lr='exact', fast=False, maxiter=it, tol=0.0).cpu()
+        xh = torch.nn.functional.conv_transpose2d(zi, g["weight"])
+        losses.append(float(0.5 * (g["x"] - xh).square().sum() + g["alpha"] * zi.abs().sum()))
+    assert losses[0] > losses[1] > losses[2]
+
+
+@pytest.mark.parametrize("n,d,k,alpha", [(300, 64, 256, 0.1), (77, 13, 37, 0.5), (200, 289, 300, 0.5),
+                                         (150, 120, 40, 0.2), (64, 300, 90, 1.0), (5, 1, 1, 0.3)])
+def test_fused_ridge_start_matches_reference_formula(dev, n, d, k, alpha):
+    """initialize_code(mode='ridge') (sparse_encode.py:28-29, utils.py:28-40) in the library: against the
+    oracle's restatement in float32 (the reference's arithmetic) and in float64."""
+    x, w = make_problem(n, d, k, seed=n + d, kind="randn")
+    got = lasso_b200.linear.initialize_code(x.to(dev), w.to(dev), alpha, "ridge")
+    assert got.shape == (n, k) and got.is_cuda
+    want32 = oracle.initialize_code(x, w, alpha, "ridge")
+    gram = w.double().T @ w.double() + alpha * torch.eye(k, dtype=torch.float64)
+    want64 = torch.linalg.solve(gram, w.double().T @ x.double().T).T
+    # min(d, k) <= 64: float64 factorisation; beyond: float32 like the reference's own Cholesky (utils.py:34)
+    assert rel_fro(got.cpu().double(), want64) <= (2e-6 if min(d, k) <= 64 else 1e-5)
+    assert rel_fro(got, want32) <= TOL
+    cpu = lasso_b200.linear.initialize_code(x, w, alpha, "ridge")           # CPU tensors in, CPU tensor out
+    assert not cpu.is_cuda and torch.equal(cpu, got.cpu())
+    # the library entry point by itself (what initialize_code uses for min(d, k) <= 64), any size up to 320
+    lib = _cabi.ridge_init(x.to(dev), w.to(dev), alpha)
+    assert rel_fro(lib.cpu().double(), want64) <= (2e-6 if min(d, k) <= 64 else 1e-5)
+
+
+def test_fused_ridge_start_not_positive_definite(dev):
+    x, w = make_problem(16, 8, 12, seed=2, kind="randn")
+    with pytest.raises(RuntimeError, match="not positive definite"):          # utils.py:35-38
+        lasso_b200.linear.initialize_code(x.to(dev), w.to(dev), -5.0, "ridge")
