@@ -187,65 +187,6 @@ __global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restri
   }
 }
 
-// m <= 64 (the usual case: d = 64): the Gram lives in shared memory, one thread per row, two
-// warps; an iteration is a 64-term dot product per thread and one block barrier.
-__global__ void __launch_bounds__(64) power_iter_small_kernel(const double* __restrict__ gram,
-                                                              int m, int iters,
-                                                              double* __restrict__ out) {
-  __shared__ double M[64 * 64];   // M[c * 64 + a] = gram[a][c] (symmetric): conflict-free reads
-  __shared__ double v[2][64];
-  __shared__ double part[2][2][2];
-  const int a = threadIdx.x, lane = a & 31, warp = a >> 5;
-  for (int e = a; e < 64 * 64; e += 64) {
-    const int c = e >> 6, r = e & 63;
-    M[e] = (r < m && c < m) ? gram[(int64_t)r * m + c] : 0.0;
-  }
-  {
-    unsigned h = (unsigned)a * 2654435761u;
-    v[0][a] = a < m ? 1.0 + 0.25 * (double)((h >> 8) & 0xffff) / 65536.0 : 0.0;
-  }
-  __syncthreads();
-  double lambda = 0.0, prev = -1.0;
-  int stable = 0, cur = 0;
-  for (int it = 0; it < iters; ++it) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < 64; c += 4) {
-      s0 = fma(M[(c + 0) * 64 + a], v[cur][c + 0], s0);
-      s1 = fma(M[(c + 1) * 64 + a], v[cur][c + 1], s1);
-      s2 = fma(M[(c + 2) * 64 + a], v[cur][c + 2], s2);
-      s3 = fma(M[(c + 3) * 64 + a], v[cur][c + 3], s3);
-    }
-    const double u = (s0 + s1) + (s2 + s3);
-    const double uu = warp_sum(u * u), uv = warp_sum(u * v[cur][a]);
-    if (lane == 0) {
-      part[it & 1][warp][0] = uu;
-      part[it & 1][warp][1] = uv;
-    }
-    __syncthreads();
-    const double nn = part[it & 1][0][0] + part[it & 1][1][0];
-    const double rayleigh = part[it & 1][0][1] + part[it & 1][1][1];   // v unit-norm for it > 0
-    const double nrm = sqrt(nn);
-    if (nrm == 0.0) {
-      lambda = 0.0;
-      break;
-    }
-    v[cur ^ 1][a] = u / nrm;
-    cur ^= 1;
-    __syncthreads();
-    if (it > 0) {
-      lambda = rayleigh;
-      if (fabs(lambda - prev) <= 1e-13 * fabs(lambda)) {
-        if (++stable >= 4) break;
-      } else {
-        stable = 0;
-      }
-      prev = lambda;
-    }
-  }
-  if (a == 0) out[0] = lambda;
-}
-
 // ---------------------------------------------------------------------------
 // K3: gram_zz = Z^T Z (k x k), gram_zx = Z^T X (k x d), float64 outputs
 // ---------------------------------------------------------------------------
@@ -696,8 +637,9 @@ int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t s
 // lambda_max of a symmetric PSD m x m matrix already in scratch[0 .. m*m) (float64); scratch layout as in
 // lipschitz_run.  Shared by the dictionary's Lipschitz constant and the convolutional one (conv_lip.cu).
 int lambda_max_run(double* scratch, int m, int iters, double* l_dev, cudaStream_t st) {
-  if (m <= 64) power_iter_small_kernel<<<1, 64, 0, st>>>(scratch, m, iters, l_dev);
-  else {
+  {
+    // (one path for every size: the float64 iteration that small dictionaries used to take was slower --
+    // 0.155 vs 0.111 ms at d = 64 -- because this GPU retires only ~3 float64 FMAs per clock and SM)
     // float region behind the doubles: two m x m ping-pong matrices + 8 traces
     float* f0 = reinterpret_cast<float*>(scratch + (size_t)m * m + 2 * (size_t)m + 8);
     float* f1 = f0 + (size_t)m * m;

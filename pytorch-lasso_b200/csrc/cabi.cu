@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/lasso_b200.h: argument checks,
 // private workspace, buffer rotation of the FISTA loop, result selection.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -167,6 +168,47 @@ class Lease {
   bool locked_ = false;
 };
 
+// Drives the resident kernel under the batch-global stop test (ista.py:64, 93-95).  The kernel cannot stop
+// in place (the sum spans all tiles), so every run records its per-iteration sums and the decision is taken
+// afterwards: `run(iters, &fell_back)` executes `iters` iterations from the start codes into z_out and leaves
+// hist[0 .. iters) on the device.
+//   * no early stop: one run of maxiter iterations, one read-back of the record;
+//   * the test fired at iteration `done` < the run's length: ONE replay with exactly `done` iterations
+//     (deterministic kernel => the codes of stopping in place);
+//   * a real tolerance and a long loop (tol_abs > 0, maxiter >= 256): probe runs of maxiter / 8 (>= 64), x4, ...
+//     iterations first, so that a solve that stops after 50 of 1000 iterations costs 64 + 50 iterations, not
+//     1000 + 50.  The default tol with the default maxiter = 10, and tol = 0, never probe.
+// Returns the number of iterations of the run whose codes are in z_out (*done_out) or sets *fell_back.
+template <typename Run>
+int resident_stop_driver(Run&& run, int maxiter, double tol_abs, const double* hist, cudaStream_t st, int* done_out,
+                         int* fell_back) {
+  int rc, run_iters = maxiter;
+  if (tol_abs > 0.0 && maxiter >= 256) run_iters = std::max(64, maxiter / 8);
+  std::vector<double> h;
+  for (;;) {
+    if ((rc = run(run_iters, fell_back))) return rc;
+    *done_out = run_iters;
+    if (*fell_back || tol_abs < 0.0) return LASSO_B200_OK;
+    h.resize((size_t)run_iters);
+    LASSO_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    LASSO_CUDA_TRY(cudaStreamSynchronize(st));
+    int stop = 0;
+    for (int i = 0; i < run_iters; ++i)
+      if (h[(size_t)i] <= tol_abs) {
+        stop = i + 1;
+        break;
+      }
+    if (stop == run_iters) return LASSO_B200_OK;        // stopped on the run's last iteration: these are the codes
+    if (stop) {                                          // stopped earlier: replay exactly that many iterations
+      if ((rc = run(stop, fell_back))) return rc;
+      *done_out = stop;
+      return LASSO_B200_OK;
+    }
+    if (run_iters == maxiter) return LASSO_B200_OK;     // ran to the end
+    run_iters = (int)std::min<int64_t>((int64_t)run_iters * 4, maxiter);
+  }
+}
+
 int check_problem(const void* x, const void* w, const void* z_out, int64_t n, int d, int k) {
   if (n < 0 || d <= 0 || k <= 0) {
     set_error("invalid shape n=%lld d=%d k=%d", (long long)n, d, k);
@@ -295,24 +337,12 @@ int fista_device_impl(Workspace* ws, const float* x, const float* weight, const 
     // a threshold of exactly 0 only asks whether anything moved; the sums are not needed then
     const int hist_mode = !need_hist ? 0 : ((delta_hist == nullptr && tol_abs == 0.0) ? 2 : 1);
     int run_iters = maxiter, fell_back = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    auto run = [&](int iters, int* fb) -> int {
       if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
-      rc = fista_res_run(x, weight, z_start, z_out, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
-                         need_hist ? hist : nullptr, hist_mode, &fell_back, st);
-      if (rc) return rc;
-      if (fell_back || pass == 1 || tol_abs < 0.0 || run_iters <= 1) break;
-      std::vector<double> h((size_t)run_iters);
-      LASSO_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
-      LASSO_CUDA_TRY(cudaStreamSynchronize(st));
-      int done = run_iters;
-      for (int i = 0; i + 1 < run_iters; ++i)
-        if (h[(size_t)i] <= tol_abs) {
-          done = i + 1;
-          break;
-        }
-      if (done == run_iters) break;
-      run_iters = done;
-    }
+      return fista_res_run(x, weight, z_start, z_out, n, d, k, lr_f, lam_f, iters, fast ? 1 : 0,
+                           need_hist ? hist : nullptr, hist_mode, fb, st);
+    };
+    if ((rc = resident_stop_driver(run, maxiter, tol_abs, hist, st, &run_iters, &fell_back))) return rc;
     if (!fell_back) {
       if (delta_hist)
         LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, hist, sizeof(double) * (size_t)maxiter,
@@ -511,6 +541,16 @@ namespace {
 // device footprint is kPipeSlots waves whatever n is (host batches larger than HBM stream through).
 // hist (device, [iters]) accumulates the stop-test record of all waves.  *fell_back = 1: an iterate
 // left the fp16 range somewhere; the caller must redo the batch on another path.
+// true when the pointer is page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)
+bool host_pinned(const void* ptr) {
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost && attr.devicePointer == ptr;
+}
+
 constexpr int kPipeSlots = 3;
 // `st` is the caller's stream (the solves run on it); the caller holds the workspace lease.
 int host_pipeline(Workspace* ws, const float* x, const float* z0, float* z_out, const float* dw, int64_t n,
@@ -628,26 +668,29 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
       z0_keep.assign(z0, z0 + (size_t)n * k);
       z_start = z0_keep.data();
     }
+    // Pinned (page-locked) host buffers are addressable from the device (unified addressing), so the
+    // resident kernel could read its x tiles and write its code tiles straight through PCIe with no
+    // staging at all.  Measured at config 2 it is SLOWER than the staged three-stream pipeline (3.80 vs
+    // 3.32 ms per 200-iteration solve): all SMs reach their tile stores together and then stall on the
+    // bus, while the copy engines of the pipeline run beside the kernels.  Kept as an opt-in
+    // (LASSO_B200_ZERO_COPY=1) for hosts where staging memory is the constraint.
+    const bool zero_copy = getenv("LASSO_B200_ZERO_COPY") != nullptr && host_pinned(x) && host_pinned(z_out) &&
+                           (z_start == nullptr || host_pinned(z_start));
     int fell_back = 0, run_iters = maxiter;
-    for (int pass = 0; pass < 2; ++pass) {
-      if ((rc = host_pipeline(ws.get(), x, z_start, z_out, dw, n, d, k, lr_f, lam_f, run_iters, fast ? 1 : 0,
-                              need_hist ? hist : nullptr, hist_mode, &fell_back, st)))
-        return rc;
-      if (fell_back || pass == 1 || tol_abs < 0.0 || run_iters <= 1) break;
-      // the stop test is batch-global (ista.py:93): take it from the recorded sums and, if it fired
-      // before maxiter, stream the batch through once more with exactly that many iterations
-      std::vector<double> h((size_t)run_iters);
-      LASSO_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
-      LASSO_CUDA_TRY(cudaStreamSynchronize(st));
-      int stop = run_iters;
-      for (int i = 0; i + 1 < run_iters; ++i)
-        if (h[(size_t)i] <= tol_abs) {
-          stop = i + 1;
-          break;
-        }
-      if (stop == run_iters) break;
-      run_iters = stop;
-    }
+    auto run = [&](int iters, int* fb) -> int {
+      int rc2;
+      if (zero_copy) {
+        if ((rc2 = fista_res_prepare(dw, d, k, lr_f, lam_f, iters, fast ? 1 : 0, st))) return rc2;
+        if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+        if ((rc2 = fista_res_launch(x, z_start, z_out, n, d, k, iters, need_hist ? hist : nullptr, hist_mode, 0, st)))
+          return rc2;
+        return fista_res_finish(fb, st);
+      }
+      if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+      return host_pipeline(ws.get(), x, z_start, z_out, dw, n, d, k, lr_f, lam_f, iters, fast ? 1 : 0,
+                           need_hist ? hist : nullptr, hist_mode, fb, st);
+    };
+    if ((rc = resident_stop_driver(run, maxiter, tol_abs, hist, st, &run_iters, &fell_back))) return rc;
     if (!fell_back) {
       if (delta_hist) {
         std::vector<double> h((size_t)maxiter, 0.0);

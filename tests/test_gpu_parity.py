@@ -286,7 +286,7 @@ def test_resident_falls_back_to_the_streaming_kernel(dev, monkeypatch):
     assert bool(torch.isfinite(got[:3]).all()) and bool(torch.isfinite(got[4:]).all())
 
 
-def test_host_pipeline_streams_waves_through_a_ring(dev):
+def test_host_pipeline_streams_waves_through_a_ring(dev, monkeypatch):
     # more waves than ring slots: chunk buffers are reused while earlier downloads are in flight;
     # the result must equal the device entry point bit for bit, with a warm start and with a stop
     # test that fires early (second pipelined pass with exactly that many iterations)
@@ -297,14 +297,33 @@ def test_host_pipeline_streams_waves_through_a_ring(dev):
     z0 = 0.05 * torch.randn(n, k, generator=g)
     xd, wd = x.to(dev), w.to(dev)
     want, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 12, True, -1.0, path="resident")
-    got, _ = _cabi.fista_host(x.pin_memory(), w, z0.pin_memory(), 0.1, lr, 12, True, -1.0, path="resident")
+    # pageable x / z0 / out: the staged three-stream pipeline
+    got, _ = _cabi.fista_host(x, w, z0, 0.1, lr, 12, True, -1.0, path="resident")
     assert torch.equal(got, want.cpu())
+    # pinned x / z0 / out: same pipeline without the driver's staging copy; with LASSO_B200_ZERO_COPY=1 the
+    # kernel reads and writes the host buffers directly (one launch, no staging at all)
+    out_pin = torch.empty(n, k).pin_memory()
+    for zero_copy in (False, True):
+        if zero_copy:
+            monkeypatch.setenv("LASSO_B200_ZERO_COPY", "1")
+        got, _ = _cabi.fista_host(x.pin_memory(), w, z0.pin_memory(), 0.1, lr, 12, True, -1.0, path="resident",
+                                  out=out_pin)
+        assert got is out_pin and torch.equal(got, want.cpu())
+    monkeypatch.delenv("LASSO_B200_ZERO_COPY")
     tol_abs = float(np.float32(n * k * 1e-3))
     want, done_d, _ = _cabi.fista_device(xd, wd, None, 0.1, lr, 300, True, tol_abs, path="resident",
                                          want_iters=True)
     got, done_h = _cabi.fista_host(x, w, None, 0.1, lr, 300, True, tol_abs, path="resident", want_iters=True)
     assert 1 < done_d < 300 and done_h == done_d
     assert torch.equal(got, want.cpu())
+    got, done_p = _cabi.fista_host(x.pin_memory(), w, None, 0.1, lr, 300, True, tol_abs, path="resident",
+                                   want_iters=True, out=out_pin)
+    assert done_p == done_d and torch.equal(got, want.cpu())
+    # probe runs (maxiter >= 256 with a real tolerance: 64, 256, ... iterations before the full length) find the
+    # same stopping iteration as one full-length run would
+    want_it = oracle.ista(x[:4096], torch.zeros(4096, k), w, alpha=0.1, lr=lr, maxiter=2000,
+                          tol=1e-3 * n / 4096, return_info=True)[1]
+    assert done_d <= 300 and want_it >= 1
 
 
 def test_resident_zero_threshold_stop_test(dev):
