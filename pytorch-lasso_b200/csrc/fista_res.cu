@@ -58,7 +58,7 @@ constexpr uint32_t kSmemBytesR = kSmemX + kTileM * kDP * 4;   // 229376
 constexpr uint32_t kColY = 0;         // y, fp32: chunks 0, 1 and half of chunks 2, 3 (the rest: registers)
 constexpr uint32_t kColS = 192;       // piece slot S: [h 32 cols][l 32 cols] = 64 atoms of y (even chunks)
 constexpr uint32_t kColQ = 256;       // piece slot Q (odd chunks)
-constexpr uint32_t kColAccR = 320;    // R = Y W^T (GEMM1); phase B overwrites it with the pieces of r [h 32][l 32]
+constexpr uint32_t kColAccR = 320;    // R = Y W^T (GEMM1); phase B overwrites it with the pieces of r, [h 8 | l 8] per k-step
 constexpr uint32_t kColAccG = 384;    // G = r W, two buffers of one 64-atom chunk (GEMM2)
 constexpr uint32_t kTmemCols = 512;
 
@@ -77,6 +77,7 @@ struct ResParams {
   const float* beta;        // [iters] momentum coefficient applied at the END of iteration i
   const ResScalars* scal;
   double* hist;             // [iters] sum |z_i - z_{i+1}| or nullptr
+  double* part;             // [iters][gridDim.x] per-CTA partial records (added into hist by res_hist_reduce_kernel)
   int* flag;                // set to 1 when an operand left the fp16 range
   volatile int* dbg;        // host-mapped debug record or nullptr
   unsigned long long* trace;   // LASSO_B200_TRACE: per-warp (clock << 8 | event) log of block 0
@@ -281,8 +282,9 @@ __device__ __noinline__ bool res_store_tile(const ResParams& p, const uint8_t* z
 //   rready     512 arrivals   pieces of r stored                   compute -> MMA
 //   gfull[q]   commit         GEMM2 chunk q complete               MMA -> set q & 1
 //   gfree[j]   256 arrivals   C(j) has G buffer j in registers     set j -> MMA (GEMM2 j + 2)
-// kHist: 0 no stop-test record, 1 hist[it] += sum |z+ - z| (ista.py:93), 2 hist[it] = 1 if any
-// z+ != z (all a threshold of exactly 0 needs; cheaper than the sum)
+// kHist: 0 no stop-test record, 1 record sum |z+ - z| (ista.py:93), 2 record "some z+ != z" (all a
+// threshold of exactly 0 needs; cheaper than the sum).  Records go to per-CTA slots part[it][cta] and are
+// added into hist[it] in a fixed order by res_hist_reduce_kernel after the launch.
 template <int NQ, int kHist>
 __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t bd = make64(off(d2_lo, qoff + pb[t] * kPiece16 + ks * 128), d2_hi);
-                  mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, (t > 0 || ks > 0) ? 1u : 0u);
+                  mma_ts<false>(t_acc, t_r + pa[t] * 8 + ks * 16, bd, idesc2, (t > 0 || ks > 0) ? 1u : 0u);
                 }
               }
             } else {
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
                 for (int ks = 0; ks < 3; ++ks) {
                   if (ks < dsteps) {
                     const uint64_t bd = make64(off(d2_lo, qoff + pb[t] * kPiece16 + ks * 128), d2_hi);
-                    mma_ts<false>(t_acc, t_r + pa[t] * 32 + ks * 8, bd, idesc2, acc_on);
+                    mma_ts<false>(t_acc, t_r + pa[t] * 8 + ks * 16, bd, idesc2, acc_on);
                     acc_on = 1;
                   }
                 }
@@ -431,15 +433,20 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           __syncwarp();
           RTRACE(16);
         }
-        if (kHist == 1 && it > 0 && lane == 0) {
-          // stop-test record of the previous iteration: the compute warps left their partial
-          // sums in shared memory before they arrived on bar_rready; ONE atomic per CTA, issued
-          // while the tensor pipe works through the four GEMM2 chunks just queued.  (Adding them up
-          // with shared-memory float64 atomics on the compute side was measured slower: 62 vs 67 k it/s.)
-          double s = 0.0;
+        if (kHist != 0 && it > 0 && lane == 0) {
+          // stop-test record of the previous iteration: the compute warps left their partial sums (mode 2:
+          // "moved" flags) in shared memory before they arrived on bar_rready.  They go to THIS CTA's slot of
+          // the per-iteration record -- 148 CTAs x 200 iterations of atomics / stores on the same few
+          // addresses cost 6 % of the kernel -- while the tensor pipe works through the GEMM2 chunks just
+          // queued; res_hist_reduce_kernel adds the slots up in a fixed order afterwards.
+          // (float adds in four chains: this GPU's float64 adds have a long latency and this thread is the one
+          // that feeds the tensor pipe; the 16 partials are float32 anyway)
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int wi = 0; wi < 16; ++wi) s += (double)hist_s[(it - 1) & 1][wi];
-          atomicAdd(p.hist + it - 1, s);
+          for (int wi = 0; wi < 16; ++wi) s4[wi & 3] += hist_s[(it - 1) & 1][wi];
+          const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          // (a reduction without return value: fire and forget, the issuing thread does not wait for the slot)
+          if (s != 0.f) atomicAdd(&p.part[(size_t)(it - 1) * gridDim.x + blockIdx.x], (double)s);
         }
         // ---- GEMM1 of the next iteration, slice by slice as the epilogue delivers the pieces ----
         if (more) {
@@ -564,11 +571,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
             split2_pair(ra, wh[2 * j], wl[2 * j]);
             split2_pair(rc, wh[2 * j + 1], wl[2 * j + 1]);
           }
-          // the pieces go where R was: every warp of the tile must have its part of R in registers
-          compute_sync();
-          const uint32_t t_r = tbase + lane_base + kColAccR + wg * 8;
+          // the pieces go where R was, k-step by k-step: the 16 features this thread read become [h 8 cols |
+          // l 8 cols] in the very columns it read them from, so no warp ever overwrites what another still
+          // has to load (the MMA takes the A operand of every k-step from its own TMEM address anyway)
+          const uint32_t t_r = tbase + lane_base + kColAccR + wg * 16;
           tmem_st8(t_r, wh);
-          tmem_st8(t_r + 32, wl);
+          tmem_st8(t_r + 8, wl);
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&bar_rready);
@@ -576,6 +584,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         }
         // ---------------- phase C (+ pieces of the next iteration) ----------------
         float part = 0.f, part_b = 0.f;   // two chains: 64 dependent adds per iteration otherwise
+        float2 moved2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int qi = 0; qi < 2; ++qi) {
           const int q = set + 2 * qi;
@@ -638,12 +647,14 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
                   const float2 c = make_float2(fminf(fmaxf(v.x, -lam), lam), fminf(fmaxf(v.y, -lam), lam));
                   const float2 zn = rsub2(v, c);
                   const float2 dl = rsub2(zn, zz);                       // z+ - z
-                  if (kHist != 0) {                                      // stop-test sum (ista.py:93)
-                    // (mode 2 only asks whether the sum is non-zero; it takes the same adds, which run
-                    // on the FMA pipe, rather than OR-ing the bit patterns on the busier ALU pipe)
+                  if (kHist == 1) {                                      // stop-test sum (ista.py:93)
                     if (h2) part_b += fabsf(dl.x) + fabsf(dl.y);
                     else part += fabsf(dl.x) + fabsf(dl.y);
                   }
+                  // mode 2 only asks whether anything moved: one packed multiply-add per pair on the FMA pipe
+                  // (sum of squares; a non-zero dl is a difference of O(1) float32 numbers in scaled units,
+                  // >= 1e-16, so its square cannot underflow) instead of OR-ing bit patterns on the ALU pipe
+                  if (kHist == 2) moved2 = __ffma2_rn(dl, dl, moved2);
                   const float2 yn = __ffma2_rn(beta2, dl, zn);           // ista.py:100
                   if (h2) { z4.z = zn.x; z4.w = zn.y; }
                   else { z4.x = zn.x; z4.y = zn.y; }
@@ -703,19 +714,13 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
           } else {
-            s = __any_sync(0xffffffffu, part + part_b > 0.f) ? 1.f : 0.f;
+            s = __any_sync(0xffffffffu, moved2.x + moved2.y > 0.f) ? 1.f : 0.f;
           }
           if (lane == 0) {
-            if (kHist == 2) {
-              // "something moved" needs no sum: a plain store of the same value from whoever saw it
-              if (s > 0.f) p.hist[it] = 1.0;
-            } else if (more) {
-              // the MMA warp adds the 16 partial records up after the next bar_rready (one atomic
-              // per CTA and iteration); nobody comes after a tile's last iteration
-              hist_s[it & 1][warp] = s;
-            } else {
-              atomicAdd(p.hist + it, (double)s);
-            }
+            // the MMA warp adds the 16 partial records up after the next bar_rready; nobody comes after a
+            // tile's last iteration, so there the warps add to the CTA's slot themselves
+            if (more) hist_s[it & 1][warp] = s;
+            else if (s != 0.f) atomicAdd(&p.part[(size_t)it * gridDim.x + blockIdx.x], (double)s);
           }
         }
         ++gi;
@@ -782,7 +787,24 @@ __global__ void res_prep_w_kernel(const float* __restrict__ w, int d, int k, con
   *reinterpret_cast<__half*>(image + kPieceBytes + off) = l;
 }
 
+// hist[it] += sum over the CTAs' slots (fixed order: the sums are reproducible run to run); slots cleared
+// for the next launch.  One warp per iteration.
+__global__ void res_hist_reduce_kernel(double* __restrict__ part, int slots, int iters, double* __restrict__ hist) {
+  const int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (it >= iters) return;
+  double* row = part + (size_t)it * slots;
+  double s = 0.0;
+  for (int c = lane; c < slots; c += 32) {
+    s += row[c];
+    row[c] = 0.0;
+  }
+  s = warp_sum(s);
+  if (lane == 0 && s != 0.0) hist[it] += s;
+}
+
 struct ResState {
+  double* part = nullptr;
+  size_t part_cap = 0;
   uint8_t* w_image = nullptr;
   ResScalars* scal = nullptr;
   int* flag = nullptr;
@@ -900,6 +922,20 @@ int fista_res_launch(const float* x, const float* z0, float* z_out, int64_t n, i
   p.beta = S.beta;
   p.scal = S.scal;
   p.hist = hist;
+  p.part = nullptr;
+  if (hist_mode != 0) {
+    // per-CTA slots of the stop-test record, [iters][grid] doubles, all zero between launches
+    const size_t need = (size_t)iters * S.num_sms;
+    if (need > S.part_cap) {
+      if (S.part) LASSO_CUDA_TRY(cudaFree(S.part));
+      S.part = nullptr;
+      S.part_cap = 0;
+      LASSO_CUDA_TRY(cudaMalloc(&S.part, sizeof(double) * need));
+      LASSO_CUDA_TRY(cudaMemsetAsync(S.part, 0, sizeof(double) * need, st));
+      S.part_cap = need;
+    }
+    p.part = S.part;
+  }
   p.flag = S.flag;
   p.dbg = S.dbg_dev;
   p.trace = trace_path ? S.trace : nullptr;
@@ -923,6 +959,11 @@ int fista_res_launch(const float* x, const float* z0, float* z_out, int64_t n, i
 #undef LASSO_RES_LAUNCH
   LASSO_CHECK_LAUNCH();
   count_launch();
+  if (hist_mode != 0) {
+    res_hist_reduce_kernel<<<(iters + 7) / 8, 256, 0, st>>>(S.part, (int)grid, iters, hist);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+  }
   return LASSO_B200_OK;
 }
 
