@@ -682,6 +682,16 @@ int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gz
   LASSO_CUDA_TRY(cudaMemsetAsync(gzz, 0, sizeof(double) * (size_t)k * k, st));
   LASSO_CUDA_TRY(cudaMemsetAsync(gzx, 0, sizeof(double) * (size_t)k * d, st));
   if (n == 0) return LASSO_B200_OK;
+  // k <= 256, d <= 128 (BASELINE configs 2, 4): fp16-split tcgen05 kernel (gram_tc.cu); everything else and
+  // small batches: the FFMA kernel below.  LASSO_B200_GRAM=ffma forces the latter (tests compare the two).
+  static void* tc_scratch[64] = {nullptr};
+  const char* force = getenv("LASSO_B200_GRAM");
+  if (gram_tc_supported(n, d, k) && !(force && force[0] == 'f')) {
+    int dev = 0;
+    LASSO_CUDA_TRY(cudaGetDevice(&dev));
+    if (!tc_scratch[dev]) LASSO_CUDA_TRY(cudaMalloc(&tc_scratch[dev], 256));
+    return gram_tc_run(z, x, n, d, k, gzz, gzx, tc_scratch[dev], st);
+  }
   const int nbi = (k + kGT - 1) / kGT, nbj = (k + d + kGT - 1) / kGT;
   dim3 grid((unsigned)((n + kGSlab - 1) / kGSlab), (unsigned)(nbi * nbj));
   gram_kernel<<<grid, 256, 0, st>>>(z, x, n, d, k, gzz, gzx);

@@ -154,6 +154,9 @@ int trial_run(const float* x, const float* point, const float* grad, const float
               int d, int k, float step, float lam, float* cand, double* sums4, cudaStream_t st);
 int momentum_run(const float* z_next, const float* z, float beta, float* y, int64_t count,
                  double* delta, cudaStream_t st);
+bool gram_tc_supported(int64_t n, int d, int k);
+int gram_tc_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz, double* gzx,
+                void* scratch, cudaStream_t st);
 int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz,
              double* gzx, cudaStream_t st);
 int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t st);

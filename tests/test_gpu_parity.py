@@ -828,3 +828,26 @@ def test_fused_ridge_start_not_positive_definite(dev):
     x, w = make_problem(16, 8, 12, seed=2, kind="randn")
     with pytest.raises(RuntimeError, match="not positive definite"):          # utils.py:35-38
         lasso_b200.linear.initialize_code(x.to(dev), w.to(dev), -5.0, "ridge")
+
+
+@pytest.mark.parametrize("n,d,k,density", [(131072, 64, 256, 0.08), (20000, 64, 256, 1.0), (9000, 24, 70, 0.1),
+                                           (5000, 128, 200, 0.3), (4100, 10, 128, 0.5)])
+def test_tensor_core_gram_statistics(dev, monkeypatch, n, d, k, density):
+    """K3 on tcgen05 (gram_tc.cu): Z^T Z and Z^T X against float64, and against the FFMA kernel it replaces for
+    k <= 256, d <= 128.  The round-toward-zero accumulate of the tensor core is confined to runs of 16
+    accumulations (two-level accumulation), which keeps the statistics within the 1e-6 they are tested to."""
+    g = torch.Generator().manual_seed(n + k)
+    z = torch.randn(n, k, generator=g) * (torch.rand(n, k, generator=g) < density) * 3.0
+    z[:, 3] = z[:, 3].abs()                    # a same-sign column: the case a truncation bias would show in
+    x = torch.randn(n, d, generator=g) * 0.25
+    zd, xd = z.to(dev), x.to(dev)
+    gzz, gzx = _cabi.gram(zd, xd)
+    monkeypatch.setenv("LASSO_B200_GRAM", "ffma")
+    fzz, fzx = _cabi.gram(zd, xd)
+    monkeypatch.delenv("LASSO_B200_GRAM")
+    z64, x64 = z.double(), x.double()
+    wzz, wzx = z64.T @ z64, z64.T @ x64
+    assert rel_fro(fzz, wzz) <= 1e-6 and rel_fro(fzx, wzx) <= 1e-6
+    assert rel_fro(gzz, wzz) <= 1e-6 and rel_fro(gzx, wzx) <= 1e-6
+    assert float((gzz.cpu() - wzz).diagonal().abs().max() / wzz.diagonal().abs().max()) <= 1e-6
+    assert torch.equal(gzz, gzz.T)             # mirrored tiles: exactly symmetric
