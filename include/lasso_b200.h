@@ -46,7 +46,7 @@ typedef enum lasso_b200_status {
 
 /* which inner-loop kernel lasso_b200_fista_f32 uses */
 typedef enum lasso_b200_path {
-  LASSO_B200_PATH_AUTO = 0,    /* resident, else k-blocked tcgen05 kernel when the shape fits, else FFMA */
+  LASSO_B200_PATH_AUTO = 0,    /* resident, else k-blocked / Gram-form tcgen05 kernel when the shape fits, else FFMA */
   LASSO_B200_PATH_FFMA = 1,    /* CUDA-core fp32 FFMA kernel: any n, d, k                    */
   LASSO_B200_PATH_TCGEN05 = 2, /* streaming tcgen05 kernel, one launch per iteration (bf16x3) */
   LASSO_B200_PATH_RESIDENT = 3, /* resident tcgen05 kernel (any d <= 64, k <= 256): all iterations
@@ -54,11 +54,16 @@ typedef enum lasso_b200_path {
                                   problem).  Synchronises the stream once per solve; falls
                                   back to LASSO_B200_PATH_TCGEN05 by itself if an iterate
                                   leaves the fp16 operand range.                               */
-  LASSO_B200_PATH_BLOCKED = 4  /* k-blocked streaming tcgen05 kernel for dictionaries that do not
+  LASSO_B200_PATH_BLOCKED = 4, /* k-blocked streaming tcgen05 kernel for dictionaries that do not
                                   fit one SM (d <= 128, k <= 1024, multiples of 4): one launch per
                                   iteration, codes and dictionary slices stream through a TMA
                                   ring.  Synchronises the stream once per solve; falls back to
                                   LASSO_B200_PATH_FFMA by itself like the resident path.        */
+  LASSO_B200_PATH_GRAM = 5     /* Gram-form tcgen05 kernel for many features and few atoms (d > 128,
+                                  k <= 320, k a multiple of 4 -- the reference notebook's d = 289,
+                                  k = 300): W^T W and x W once per solve, then one GEMM per
+                                  iteration with y resident in TMEM.  Same synchronisation and
+                                  fallback behaviour as LASSO_B200_PATH_BLOCKED.               */
 } lasso_b200_path;
 
 /* ABI version: major*1000 + minor */

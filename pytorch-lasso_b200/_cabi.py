@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # LASSO_B200_LIB: load another build of the library (kernel variants, tools/variants.sh)
 LIB_PATH = os.environ.get("LASSO_B200_LIB") or os.path.join(_HERE, "csrc", "liblasso_b200.so")
 
-PATH_AUTO, PATH_FFMA, PATH_TCGEN05, PATH_RESIDENT, PATH_BLOCKED = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_FFMA, PATH_TCGEN05, PATH_RESIDENT, PATH_BLOCKED, PATH_GRAM = 0, 1, 2, 3, 4, 5
 _PATH_NAMES = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tcgen05": PATH_TCGEN05,
-               "resident": PATH_RESIDENT, "blocked": PATH_BLOCKED}
+               "resident": PATH_RESIDENT, "blocked": PATH_BLOCKED, "gram": PATH_GRAM}
 
 EXPORTS = (
     "lasso_b200_version",

@@ -243,7 +243,8 @@ int64_t lasso_b200_resident_fallbacks(void) { return (int64_t)g_res_fallbacks.lo
 int32_t lasso_b200_select_path(int64_t n, int32_t d, int32_t k) {
   if (fista_res_supported(n, d, k)) return LASSO_B200_PATH_RESIDENT;
   if (fista_tc_supported(n, d, k)) return LASSO_B200_PATH_TCGEN05;
-  return fista_blk_supported(n, d, k) ? LASSO_B200_PATH_BLOCKED : LASSO_B200_PATH_FFMA;
+  if (fista_blk_supported(n, d, k)) return LASSO_B200_PATH_BLOCKED;
+  return fista_gram_supported(n, d, k) ? LASSO_B200_PATH_GRAM : LASSO_B200_PATH_FFMA;
 }
 
 }  // extern "C" (reopened below)
@@ -277,13 +278,14 @@ int32_t lasso_b200_fista_f32(const float* x, const float* weight, const float* z
   }
   if (path == LASSO_B200_PATH_AUTO) path = lasso_b200_select_path(n, d, k);
   if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05 &&
-      path != LASSO_B200_PATH_RESIDENT && path != LASSO_B200_PATH_BLOCKED) {
+      path != LASSO_B200_PATH_RESIDENT && path != LASSO_B200_PATH_BLOCKED && path != LASSO_B200_PATH_GRAM) {
     set_error("unknown path %d", path);
     return LASSO_B200_ERR_INVALID;
   }
   if ((path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) ||
       (path == LASSO_B200_PATH_RESIDENT && !fista_res_supported(n, d, k)) ||
-      (path == LASSO_B200_PATH_BLOCKED && !fista_blk_supported(n, d, k))) {
+      (path == LASSO_B200_PATH_BLOCKED && !fista_blk_supported(n, d, k)) ||
+      (path == LASSO_B200_PATH_GRAM && !fista_gram_supported(n, d, k))) {
     set_error("tcgen05 paths do not take n=%lld d=%d k=%d", (long long)n, d, k);
     return LASSO_B200_ERR_UNSUPPORTED;
   }
@@ -355,6 +357,64 @@ int fista_device_impl(Workspace* ws, const float* x, const float* weight, const 
     path = fista_tc_supported(n, d, k) ? LASSO_B200_PATH_TCGEN05 : LASSO_B200_PATH_FFMA;
   }
 
+  if (path == LASSO_B200_PATH_GRAM) {
+    // Gram-form kernel (fista_gram.cu): all iterations of a tile in one launch, so -- like the resident path -- the
+    // batch-global stop test is taken afterwards from the recorded sums and a run that should have stopped early
+    // is replayed with exactly that many iterations.  z_i lives in (i even ? A : B); A, B are chosen per run so
+    // that the last iterate lands in z_out.  Start codes that alias z_out are stashed first.
+    float* wsbuf = (float*)ws->code.ptr;
+    float* stash = nullptr;
+    const float* z_start = z0;
+    if (z0 != nullptr && z0 == z_out) {
+      LASSO_CUDA_TRY(cudaMallocAsync((void**)&stash, code_bytes, st));
+      LASSO_CUDA_TRY(cudaMemcpyAsync(stash, z0, code_bytes, cudaMemcpyDeviceToDevice, st));
+      z_start = stash;
+    }
+    const bool need_hist = tol_abs >= 0.0 || delta_hist != nullptr;
+    int run_iters = maxiter, fell_back = 0;
+    auto run = [&](int iters, int* fb) -> int {
+      FistaArgs a{};
+      a.x = x;
+      a.w = weight;
+      a.z_a = (iters & 1) ? wsbuf : z_out;
+      a.z_b = (iters & 1) ? z_out : wsbuf;
+      a.n = n;
+      a.d = d;
+      a.k = k;
+      a.lr = lr_f;
+      a.lam = lam_f;
+      a.maxiter = iters;
+      a.fast = fast ? 1 : 0;
+      a.tol_abs = tol_abs;
+      a.hist = hist;
+      a.record = need_hist ? 1 : 0;
+      if (z_start == nullptr) LASSO_CUDA_TRY(cudaMemsetAsync(a.z_a, 0, code_bytes, st));
+      else LASSO_CUDA_TRY(cudaMemcpyAsync(a.z_a, z_start, code_bytes, cudaMemcpyDeviceToDevice, st));
+      if (need_hist) LASSO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)maxiter, st));
+      return fista_gram_run(a, fb, st);
+    };
+    rc = resident_stop_driver(run, maxiter, tol_abs, hist, st, &run_iters, &fell_back);
+    if (!rc && !fell_back) {
+      if (stash) cudaFreeAsync(stash, st);
+      if (delta_hist)
+        LASSO_CUDA_TRY(cudaMemcpyAsync(delta_hist, hist, sizeof(double) * (size_t)maxiter,
+                                       cudaMemcpyDeviceToDevice, st));
+      if (iters_done) *iters_done = run_iters;
+      return LASSO_B200_OK;
+    }
+    if (rc) {
+      if (stash) cudaFreeAsync(stash, st);
+      return rc;
+    }
+    // an iterate left the fp16 operand range: the exact-fp32 FFMA kernel solves the batch from the start codes
+    g_res_fallbacks.fetch_add(1, std::memory_order_relaxed);
+    if (stash) {
+      LASSO_CUDA_TRY(cudaMemcpyAsync(z_out, stash, code_bytes, cudaMemcpyDeviceToDevice, st));
+      cudaFreeAsync(stash, st);     // (stream-ordered: the copy above is enqueued first)
+    }
+    path = LASSO_B200_PATH_FFMA;
+  }
+
   // z_i lives in (i even ? z_a : z_b); put z_maxiter into z_out without a copy
   float* wsbuf = (float*)ws->code.ptr;
   float* z_a = (maxiter & 1) ? wsbuf : z_out;
@@ -379,6 +439,7 @@ int fista_device_impl(Workspace* ws, const float* x, const float* weight, const 
   a.tol_abs = tol_abs;
   a.hist = hist;
   a.zero_start = z0 == nullptr ? 1 : 0;
+  a.record = (tol_abs >= 0.0 || delta_hist != nullptr) ? 1 : 0;
   if (path == LASSO_B200_PATH_BLOCKED) {
     // like the resident path: an iterate beyond the fp16 operand range hands the batch to the FFMA
     // kernel, which needs the start codes again (they may alias z_out)
@@ -724,7 +785,7 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
     done = 0;
   } else {
     if (path != LASSO_B200_PATH_FFMA && path != LASSO_B200_PATH_TCGEN05 && path != LASSO_B200_PATH_RESIDENT &&
-        path != LASSO_B200_PATH_BLOCKED) {
+        path != LASSO_B200_PATH_BLOCKED && path != LASSO_B200_PATH_GRAM) {
       set_error("unknown path %d", path);
       return LASSO_B200_ERR_INVALID;
     }
@@ -734,7 +795,8 @@ int32_t lasso_b200_fista_f32_host(const float* x, const float* weight, const flo
     }
     if ((path == LASSO_B200_PATH_TCGEN05 && !fista_tc_supported(n, d, k)) ||
         (path == LASSO_B200_PATH_RESIDENT && !fista_res_supported(n, d, k)) ||
-        (path == LASSO_B200_PATH_BLOCKED && !fista_blk_supported(n, d, k))) {
+        (path == LASSO_B200_PATH_BLOCKED && !fista_blk_supported(n, d, k)) ||
+        (path == LASSO_B200_PATH_GRAM && !fista_gram_supported(n, d, k))) {
       set_error("tcgen05 paths do not take n=%lld d=%d k=%d", (long long)n, d, k);
       return LASSO_B200_ERR_UNSUPPORTED;
     }

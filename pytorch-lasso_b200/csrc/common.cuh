@@ -97,6 +97,7 @@ struct FistaArgs {
   double tol_abs;
   double* hist;  // [maxiter] device, zero-initialised
   int zero_start = 0;  // z_a holds the all-zero start (kernels that rescale the codes may skip it)
+  int record = 1;      // 0: nobody reads hist (no stop test, no history asked for); kernels may skip the sums
 };
 
 // scale factors of the resident kernel (fista_res.cu): all powers of two
@@ -121,6 +122,8 @@ struct ConvShape {
 bool fista_blk_supported(int64_t n, int d, int k);
 bool conv2d_blk_supported(const ConvShape& c, int k);
 int fista_blk_run(const FistaArgs& a, int* fell_back, cudaStream_t st, const ConvShape* conv = nullptr);
+bool fista_gram_supported(int64_t n, int d, int k);
+int fista_gram_run(const FistaArgs& a, int* fell_back, cudaStream_t st);
 bool fista_res_supported(int64_t n, int d, int k);
 int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int iters, int fast,
                       cudaStream_t st);

@@ -229,6 +229,85 @@ def test_blocked_kernel_warm_start_stop_test_and_fallback(dev, monkeypatch):
     assert torch.equal(got, ffma)
 
 
+@pytest.mark.parametrize("n,d,k,kind,alpha,iters,fast", [
+    (1000, 289, 300, "planted", 0.5, 20, True),   # the reference notebook's dictionary and solver settings
+    (700, 289, 300, "randn", 0.1, 60, True),
+    (513, 200, 132, "randn", 0.2, 30, False),     # plain ISTA, last slab and last k-step partly empty
+    (300, 512, 320, "planted", 0.1, 40, True),    # the largest dictionary whose pieces fit TMEM
+    (130, 129, 4, "randn", 0.1, 25, True),        # one k-step, one slab
+    (20000, 160, 64, "planted", 0.1, 3, True),    # more tiles than SMs: several tiles per CTA
+])
+def test_gram_form_kernel_matches_oracle(dev, n, d, k, kind, alpha, iters, fast):
+    """fista_gram.cu (d > 128, k <= 320): g = y (W^T W) - x W on tcgen05 against the oracle's two-GEMM float32 loop."""
+    assert _cabi.select_path(n, d, k) == _cabi.PATH_GRAM
+    fallbacks = _cabi.resident_fallbacks()
+    x, w = make_problem(n, d, k, seed=2, kind=kind)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    rows = slice(0, n) if n <= 2000 else slice(n - 700, n)        # the oracle on a row subset of the big case
+    xd, wd = x.to(dev), w.to(dev)
+    got = ista(xd, torch.zeros(n, k, device=dev), wd, alpha=alpha, fast=fast, lr=lr, maxiter=iters, tol=0.0)   # auto
+    want = oracle.ista(x[rows], torch.zeros(x[rows].size(0), k), w, alpha=alpha, fast=fast, lr=lr,
+                       maxiter=iters, tol=0.0)
+    assert rel_fro(got[rows], want) <= TOL
+    assert support_mismatch(got[rows].cpu(), want) <= 2e-3
+    assert _cabi.resident_fallbacks() == fallbacks      # solved by the tensor-core kernel itself
+    ffma, _, _ = _cabi.fista_device(xd, wd, None, alpha, lr, iters, fast, -1.0, path="ffma")
+    assert rel_fro(got, ffma) <= TOL
+    # shapes it must leave to the FFMA kernel: k beyond the TMEM piece columns, k not a multiple of 4
+    assert _cabi.select_path(n, 289, 324) == _cabi.PATH_FFMA
+    assert _cabi.select_path(n, 289, 298) == _cabi.PATH_FFMA
+
+
+def test_gram_form_kernel_warm_start_stop_test_and_fallback(dev, monkeypatch):
+    g = load_golden("r2_notebook_289x300")
+    z = run_case(g, dev, "gram")
+    assert rel_fro(z, g["z"]) <= TOL
+    n, d, k = 900, 289, 300
+    x, w = make_problem(n, d, k, seed=3)
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    xd, wd = x.to(dev), w.to(dev)
+    gen = torch.Generator().manual_seed(5)
+    z0 = 0.05 * torch.randn(n, k, generator=gen)
+    for fast in (True, False):
+        got, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 21, fast, -1.0, path="gram")
+        want = oracle.ista(x, z0, w, alpha=0.1, fast=fast, lr=lr, maxiter=21, tol=0.0)
+        assert rel_fro(got, want) <= TOL
+    # batch-global stop test: all iterations run in one launch, the count comes from the recorded sums and the
+    # run is replayed with it -- same count, history and codes as the FFMA kernel, which stops in place
+    tol_abs = float(np.float32(n * k * 1e-3))
+    zb, it_b, hb = _cabi.fista_device(xd, wd, None, 0.1, lr, 400, True, tol_abs, path="gram",
+                                      want_iters=True, want_hist=True)
+    zf, it_f, hf = _cabi.fista_device(xd, wd, None, 0.1, lr, 400, True, tol_abs, path="ffma",
+                                      want_iters=True, want_hist=True)
+    assert 1 < it_b < 400 and it_b == it_f and rel_fro(zb, zf) <= TOL
+    np.testing.assert_allclose(hb.cpu().numpy()[:it_b - 1], hf.cpu().numpy()[:it_b - 1], rtol=1e-4)
+    assert float(hb[it_b - 1]) <= tol_abs < float(hb[it_b - 2])
+    want, done, _ = oracle.ista(x, torch.zeros(n, k), w, alpha=0.1, lr=lr, maxiter=400, tol=1e-3, return_info=True)
+    assert done == it_b and rel_fro(zb, want) <= TOL
+    # in place over the start buffer (odd and even iteration counts put z_out on either side of the ping-pong)
+    for iters in (8, 9):
+        buf = z0.to(dev).clone()
+        got, _, _ = _cabi.fista_device(xd, wd, buf, 0.1, lr, iters, True, -1.0, path="gram", out=buf)
+        assert got.data_ptr() == buf.data_ptr()
+        want = oracle.ista(x, z0, w, alpha=0.1, lr=lr, maxiter=iters, tol=0.0)
+        assert rel_fro(got, want) <= TOL
+    # the hand-over to the FFMA kernel from the intact start codes
+    before = _cabi.resident_fallbacks()
+    monkeypatch.setenv("LASSO_B200_RES_LIMIT", "1e-3")
+    buf = z0.to(dev).clone()
+    got, _, _ = _cabi.fista_device(xd, wd, buf, 0.1, lr, 9, True, -1.0, path="gram", out=buf)
+    monkeypatch.delenv("LASSO_B200_RES_LIMIT")
+    assert _cabi.resident_fallbacks() == before + 1
+    ffma, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 9, True, -1.0, path="ffma")
+    assert torch.equal(got, ffma)
+    # rows at wildly different scales: every row is rescaled on its own
+    scale = 10.0 ** (8 * torch.rand(n, 1, generator=gen) - 4)
+    got = ista(xd * scale.to(dev), torch.zeros(n, k, device=dev), wd, alpha=0.1, lr=lr, maxiter=30, tol=0.0)
+    want = oracle.ista_f64((x * scale).double().numpy(), np.zeros((n, k)), w.double().numpy(), 0.1, lr, 30)
+    err = (got.double().cpu() - torch.from_numpy(want)).norm(dim=1) / torch.from_numpy(want).norm(dim=1).clamp_min(1e-30)
+    assert float(err.max()) <= 5e-5 and float(err.median()) <= TOL
+
+
 def test_resident_rows_at_wildly_different_scales(dev):
     # every row is its own lasso problem and is rescaled on its own: the relative error of EACH
     # row stays at the float32 level although the batch spans 12 orders of magnitude
