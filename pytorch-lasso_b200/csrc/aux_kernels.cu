@@ -41,41 +41,68 @@ __global__ void small_gram_kernel(const float* __restrict__ w, int d, int k, int
   if (a < m && b < m) gram[(int64_t)a * m + b] = acc;
 }
 
-// m > 64.  The leading eigenvector is found in float32 -- this GPU issues only a few float64
-// operations per clock, and the Rayleigh quotient is second order in the vector error, so a
-// float32-converged vector (error ~1e-6) gives the eigenvalue to ~1e-11 -- and not on G but on
-// G^16 (four trace-normalised squarings, gram_square_kernel): same eigenvectors, the eigenvalue
-// ratio that sets the convergence rate raised to the 16th power, so ~40 iterations do what ~600
-// did (each one streams the m x m matrix through a single SM).  ONE float64 matrix-vector product
-// with the original Gram and a Rayleigh quotient finish.  10.1 ms -> 0.4 ms at m = 289.
-constexpr int kSqTile = 16;
-// C = (A / tr_in) (A / tr_in) for a symmetric m x m matrix; tr_out += trace(C).  A_dbl != nullptr:
-// first squaring, the input is the float64 Gram itself.
-__global__ void gram_square_kernel(const float* __restrict__ a_f, const double* __restrict__ a_dbl, int m,
-                                   const float* __restrict__ tr_in, float* __restrict__ c,
-                                   float* __restrict__ tr_out) {
-  __shared__ float ta[kSqTile][kSqTile + 1], tb[kSqTile][kSqTile + 1];
+// The leading eigenvector is found in float32 -- this GPU issues only a few float64 operations per clock, and
+// the Rayleigh quotient is second order in the vector error, so a float32-converged vector (error ~1e-6) gives
+// the eigenvalue to ~1e-11 -- and not on G but on G^4096 (twelve trace-normalised squarings, gram_square_kernel):
+// same eigenvectors, the eigenvalue ratio that sets the convergence rate raised to the 4096th power.  A learned
+// dictionary's two largest eigenvalues are often within 0.05 % of each other: on G^16 (what this used until the
+// notebook workload was profiled) that ran all 2000 iterations, 3.4 ms per EM step at m = 289, each iteration
+// streaming the m x m matrix through a single SM; on G^4096 the same pair converges in ~10, and the iteration
+// count is capped at 256: with relative gap g the quotient is off by g exp(-2 * 4096 * 256 g) <= 1.8e-7 at worst.  Rounding in the
+// squarings perturbs the vector by ~eps / gap, the Rayleigh quotient by at most min(gap, eps^2 / gap) <= eps.
+// ONE float64 matrix-vector product with the original Gram and a Rayleigh quotient finish.
+constexpr int kSqTile = 32;       // output tile of a block of 16 x 16 threads (2 x 2 outputs each)
+constexpr int kSquarings = 12;
+constexpr int kPowerIterCap = 256;   // on G^4096: the Rayleigh quotient is then within 1 / (2 * 4096 * 256 * e) = 1.8e-7 for ANY gap
+constexpr int kTraceSlots = 32;
+// C = (A / tr_in) (A / tr_in) for a symmetric m x m matrix; tr_out += trace(C).  a_dbl != nullptr: first
+// squaring, the input is the float64 Gram itself.  C = A A^T for symmetric A, so both operand tiles are rows of A
+// (coalesced), only blocks on or above the diagonal are computed and the others are mirrored on the store.
+__global__ void __launch_bounds__(256) gram_square_kernel(const float* __restrict__ a_f, const double* __restrict__ a_dbl,
+                                                          int m, const float* __restrict__ tr_in, float* __restrict__ c,
+                                                          float* __restrict__ tr_out) {
+  if (blockIdx.x < blockIdx.y) return;
+  __shared__ float ta[kSqTile][17], tb[kSqTile][17];
   const float scale = 1.0f / fmaxf(tr_in[0], 1e-30f);
-  const int row = blockIdx.y * kSqTile + threadIdx.y, col = blockIdx.x * kSqTile + threadIdx.x;
-  float acc = 0.f;
-  for (int k0 = 0; k0 < m; k0 += kSqTile) {
-    const int ka = k0 + threadIdx.x, kb = k0 + threadIdx.y;
-    float va = 0.f, vb = 0.f;
-    if (row < m && ka < m) va = a_dbl ? (float)a_dbl[(int64_t)row * m + ka] : a_f[(int64_t)row * m + ka];
-    if (kb < m && col < m) vb = a_dbl ? (float)a_dbl[(int64_t)kb * m + col] : a_f[(int64_t)kb * m + col];
-    ta[threadIdx.y][threadIdx.x] = va * scale;
-    tb[threadIdx.y][threadIdx.x] = vb * scale;
+  const int i0 = blockIdx.y * kSqTile, j0 = blockIdx.x * kSqTile;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < m; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int r = ty + 16 * e, kk = k0 + tx;
+      float va = 0.f, vb = 0.f;
+      if (kk < m) {
+        if (i0 + r < m) va = a_dbl ? (float)a_dbl[(int64_t)(i0 + r) * m + kk] : a_f[(int64_t)(i0 + r) * m + kk];
+        if (j0 + r < m) vb = a_dbl ? (float)a_dbl[(int64_t)(j0 + r) * m + kk] : a_f[(int64_t)(j0 + r) * m + kk];
+      }
+      ta[r][tx] = va * scale;
+      tb[r][tx] = vb * scale;
+    }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < kSqTile; ++kk) acc = fmaf(ta[threadIdx.y][kk], tb[kk][threadIdx.x], acc);
+    for (int kk = 0; kk < 16; ++kk) {
+      const float a0 = ta[ty][kk], a1 = ta[ty + 16][kk], b0 = tb[tx][kk], b1 = tb[tx + 16][kk];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
     __syncthreads();
   }
-  if (row < m && col < m) {
-    c[(int64_t)row * m + col] = acc;
-    if (row == col) atomicAdd(tr_out, acc);
-  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const int i = i0 + ty + 16 * e, j = j0 + tx + 16 * f;
+      if (i < m && j < m) {
+        c[(int64_t)i * m + j] = acc[e][f];
+        if (blockIdx.x != blockIdx.y) c[(int64_t)j * m + i] = acc[e][f];
+        if (i == j) atomicAdd(tr_out, acc[e][f]);
+      }
+    }
 }
-// tr[0] = trace of the float64 Gram (as float), tr[1..4] = 0
+// tr[0] = trace of the float64 Gram (as float), the other slots = 0
 __global__ void gram_trace_kernel(const double* __restrict__ gram, int m, float* __restrict__ tr) {
   double s = 0.0;
   for (int a = threadIdx.x; a < m; a += blockDim.x) s += gram[(int64_t)a * m + a];
@@ -87,7 +114,7 @@ __global__ void gram_trace_kernel(const double* __restrict__ gram, int m, float*
     double t = 0.0;
     for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += red[wi];
     tr[0] = (float)t;
-    for (int i = 1; i < 8; ++i) tr[i] = 0.f;
+    for (int i = 1; i < kTraceSlots; ++i) tr[i] = 0.f;
   }
 }
 __global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restrict__ gram, int m,
@@ -108,19 +135,34 @@ __global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restri
   __syncthreads();
   int calm = 0;
   for (int it = 0; it < iters; ++it) {
-    for (int a = warp; a < m; a += nwarps) {
-      const float* row = gram_f + (int64_t)a * m;
-      float s0 = 0.f, s1 = 0.f;
-      int c = lane;
-      for (; c + 32 < m; c += 64) {
-        s0 = fmaf(row[c], v[c], s0);
-        s1 = fmaf(row[c + 32], v[c + 32], s1);
-      }
-      if (c < m) s0 = fmaf(row[c], v[c], s0);
-      float s = s0 + s1;
+    // four rows x four 32-column steps per warp at a time: 16 independent loads per lane in flight, so one L2
+    // latency covers 2 KB per warp (a dependent load per step made an iteration cost 18 us at m = 289)
+    for (int a = warp; a < m; a += 4 * nwarps) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c0 = lane; c0 < m; c0 += 128) {
+        float g[4][4], vc[4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) u[a] = s;
+        for (int j = 0; j < 4; ++j) {
+          const int cc = c0 + 32 * j;
+          vc[j] = cc < m ? v[cc] : 0.f;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int ar = a + r * nwarps;
+            g[r][j] = (cc < m && ar < m) ? gram_f[(int64_t)ar * m + cc] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = fmaf(g[r][j], vc[j], acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float sr = acc[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        if (lane == 0 && a + r * nwarps < m) u[a + r * nwarps] = sr;
+      }
     }
     __syncthreads();
     float part = 0.f;
@@ -156,7 +198,7 @@ __global__ void __launch_bounds__(1024) power_iter_kernel(const double* __restri
     __syncthreads();
     // components of a unit vector are O(m^-1/2): stop when none moves by more than float32 noise
     if (s_dv <= 4e-7f) {
-      if (++calm >= 8) break;
+      if (++calm >= 3) break;
     } else {
       calm = 0;
     }
@@ -640,19 +682,22 @@ int lambda_max_run(double* scratch, int m, int iters, double* l_dev, cudaStream_
   {
     // (one path for every size: the float64 iteration that small dictionaries used to take was slower --
     // 0.155 vs 0.111 ms at d = 64 -- because this GPU retires only ~3 float64 FMAs per clock and SM)
-    // float region behind the doubles: two m x m ping-pong matrices + 8 traces
+    // float region behind the doubles: two m x m ping-pong matrices + the traces
     float* f0 = reinterpret_cast<float*>(scratch + (size_t)m * m + 2 * (size_t)m + 8);
     float* f1 = f0 + (size_t)m * m;
     float* tr = f1 + (size_t)m * m;
     gram_trace_kernel<<<1, 256, 0, st>>>(scratch, m, tr);
-    dim3 sgrid((m + kSqTile - 1) / kSqTile, (m + kSqTile - 1) / kSqTile), sblock(kSqTile, kSqTile);
-    gram_square_kernel<<<sgrid, sblock, 0, st>>>(nullptr, scratch, m, tr + 0, f0, tr + 1);   // G^2
-    gram_square_kernel<<<sgrid, sblock, 0, st>>>(f0, nullptr, m, tr + 1, f1, tr + 2);        // G^4
-    gram_square_kernel<<<sgrid, sblock, 0, st>>>(f1, nullptr, m, tr + 2, f0, tr + 3);        // G^8
-    gram_square_kernel<<<sgrid, sblock, 0, st>>>(f0, nullptr, m, tr + 3, f1, tr + 4);        // G^16
+    dim3 sgrid((m + kSqTile - 1) / kSqTile, (m + kSqTile - 1) / kSqTile), sblock(16, 16);
+    const float* src = nullptr;
+    float* dst = f0;
+    for (int sq = 0; sq < kSquarings; ++sq) {                     // G^2, G^4, ... G^4096
+      gram_square_kernel<<<sgrid, sblock, 0, st>>>(src, sq == 0 ? scratch : nullptr, m, tr + sq, dst, tr + sq + 1);
+      src = dst;
+      dst = dst == f0 ? f1 : f0;
+    }
     LASSO_CHECK_LAUNCH();
-    count_launch(5);
-    power_iter_kernel<<<1, 1024, 2 * (size_t)m * sizeof(float), st>>>(scratch, m, iters, f1, l_dev);
+    count_launch(1 + kSquarings);
+    power_iter_kernel<<<1, 1024, 2 * (size_t)m * sizeof(float), st>>>(scratch, m, std::min(iters, kPowerIterCap), src, l_dev);
   }
   LASSO_CHECK_LAUNCH();
   count_launch();
@@ -661,12 +706,12 @@ int lambda_max_run(double* scratch, int m, int iters, double* l_dev, cudaStream_
 
 // doubles needed by lambda_max_run for an m x m matrix (incl. the result slot behind the Gram)
 size_t lambda_max_scratch_doubles(int m) {
-  return (size_t)m * m + 2 * (size_t)m + 8 + ((2 * (size_t)m * m + 8) * sizeof(float) + 7) / 8;
+  return (size_t)m * m + 2 * (size_t)m + 8 + ((2 * (size_t)m * m + kTraceSlots) * sizeof(float) + 7) / 8;
 }
 
 int lipschitz_run(const float* w, int d, int k, int iters, double* l_dev, double* scratch,
                   cudaStream_t st) {
-  // scratch (doubles): [m*m] Gram | [2*m] spare | [8] result | then floats: 2 x [m*m] powers of the Gram, [8] traces
+  // scratch (doubles): [m*m] Gram | [2*m] spare | [8] result | then floats: 2 x [m*m] powers of the Gram, the traces
   const int row_gram = d <= k ? 1 : 0;
   const int m = row_gram ? d : k;
   const int len = row_gram ? k : d;

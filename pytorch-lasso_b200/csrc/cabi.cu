@@ -829,8 +829,7 @@ int32_t lasso_b200_lipschitz_f32(const float* weight, int32_t d, int32_t k, int3
   Lease ws;
   int rc = ws.acquire(st);
   if (rc) return rc;
-  if ((rc = ensure(ws->scratch, sizeof(double) * ((size_t)m * m + 2 * (size_t)m + 8) + sizeof(float) * (2 * (size_t)m * m + 8))))
-    return rc;
+  if ((rc = ensure(ws->scratch, sizeof(double) * lambda_max_scratch_doubles(m)))) return rc;
   double* scratch = (double*)ws->scratch.ptr;
   double* l_dev = scratch + (size_t)m * m + 2 * (size_t)m;
   if ((rc = lipschitz_run(weight, d, k, iters, l_dev, scratch, st))) return rc;
