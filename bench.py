@@ -25,6 +25,7 @@ lr pinned, tol=0 -- BASELINE.md section 4).  Prints ONE JSON line (rank 0).
   dict_learning_c4   BASELINE config 4: ms per EM step at 131072 rows per rank (100 FISTA iterations,
             Gram statistics, ONE all-reduce, replicated atom sweep), the all-reduce timed by itself
   gpu_eager_baseline  the reference's loop as stock torch ops on the same B200 (N = 1 only)
+  notebook_dict_learning  EM steps/s at the shapes of the reference's notebook (its only published numbers), N = 1 only
   e2e_roofline        pinned H2D / D2H bandwidth per rank and the time the step's copies need alone
 """
 from __future__ import annotations
@@ -409,6 +410,30 @@ def run_ours(args, rank, local_rank, world):
                 "same atom sweep on every rank; all_reduce_us = CUDA events around that collective"}
     del x4
 
+    # ---- the reference's only published workload: the Omniglot notebook's dict_learning (d=289, k=300) ----
+    notebook = None
+    if world == 1:
+        from lasso_b200.testing import make_problem as _mk
+        xn, _ = _mk(10000, 289, 300, seed=0, kind="planted", density=0.05)
+        xn = (xn * 3.0).to(dev)
+        nb_steps = 20
+        notebook = {"workload": "examples/dict_learning_omniglot.ipynb shapes on synthetic planted data: n=10000 d=289 "
+                                "k=300 alpha=0.5, ISTA init=ridge maxiter=20 fast lr=auto; E-step on the Gram-form "
+                                "tcgen05 kernel (fista_gram.cu)",
+                    "published_reference_em_steps_per_s": {"constrained": 8.81, "unconstrained": 33.14,
+                                                           "hardware": "unnamed CUDA GPU (notebook output)"}}
+        for name, kw in (("constrained", dict(constrained=True)), ("unconstrained", dict(constrained=False, lambd=2e-2))):
+            for rep in range(2):
+                torch.manual_seed(0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dl_fn(xn, 300, alpha=0.5, steps=nb_steps, device=str(dev), progbar=False, algorithm="ista",
+                      init="ridge", maxiter=20, fast=True, lr="auto", **kw)
+                torch.cuda.synchronize()
+                dt_nb = time.perf_counter() - t0
+            notebook[name + "_em_steps_per_s"] = nb_steps / dt_nb
+        del xn
+
     # ---- the reference's loop as stock torch ops on this B200 (cuBLAS fp32, 13 launches + 1 sync / iteration) ----
     gpu_eager = None
     if world == 1:
@@ -501,6 +526,8 @@ def run_ours(args, rank, local_rank, world):
             "dict_learning_c4": dict_learning_c4,
             "e2e_roofline": e2e_roofline,
         }
+        if notebook is not None:
+            line["notebook_dict_learning"] = notebook
         if gpu_eager is not None:
             line["gpu_eager_baseline"] = gpu_eager
         if world == 1 and not args.no_cpu_baseline:

@@ -28,7 +28,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <unistd.h>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -59,7 +58,6 @@ struct GramTcParams {
   const float* scales;      // [0] = sz, [1] = sx (powers of two), [2] = 1/sz^2, [3] = 1/(sz sx)
   double* gzz;
   double* gzx;
-  volatile int* dbg;
 };
 
 #define GT_WAIT(bar, parity)                                                              \
@@ -75,11 +73,7 @@ struct GramTcParams {
           : "r"(_addr), "r"(_par), "r"(20000u)                                            \
           : "memory");                                                                    \
       if (_ok) break;                                                                     \
-      if (++_n > (1u << 17)) {           /* a protocol bug must not hang the GPU */       \
-        printf("gram_tc wait timeout: line %d block %d thread %d parity %u\n", __LINE__,    \
-               (int)blockIdx.x, (int)threadIdx.x, _par);                                  \
-        __trap();                                                                         \
-      }                                                                                   \
+      if (++_n > (1u << 17)) __trap();   /* a protocol bug must not hang the GPU */       \
     }                                                                                     \
   } while (0)
 
@@ -129,24 +123,19 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
-  if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 0] = 1 + nblocks;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
-  if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 1] = 1;
-#define GT_MARK(slot, v) do { if (p.dbg && lane == 0 && (warp == 16 || warp == 0)) p.dbg[blockIdx.x * 8 + (slot)] = (v); } while (0)
 
   if (warp == 16) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(kFmtF16, 128, 128, 0, 1);   // A from TMEM, B MN-major, N = 128
     for (int b = 0; b < nblocks; ++b) {
       const uint32_t s = (uint32_t)b & 1u;
-      GT_MARK(2, 100 * b + 1);
       GT_WAIT(&bar_full[s], ((uint32_t)b >> 1) & 1u);
       // every block is its own level-1 run: L / C are overwritten, so the previous run must have been folded
       if (b > 0) GT_WAIT(&bar_accfree, ((uint32_t)b - 1u) & 1u);
-      GT_MARK(2, 100 * b + 2);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t desc = make_smem_desc_sw128(smem_u32(smem + s * kGtStage), kGtSlab, 1024);
@@ -166,9 +155,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
         mma_commit(&bar_accfull);
       }
       __syncwarp();
-      GT_MARK(2, 100 * b + 3);
     }
-    GT_MARK(2, 99999);
   } else {
     // ===================== compute warps: operand conversion, level-2 accumulation, flush =====================
     const int quad = warp & 3, wg = warp >> 2;
@@ -244,10 +231,8 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
       convert(0);
     }
     for (int b = 0; b < nblocks; ++b) {
-      GT_MARK(3, 100 * b + 1);
       // block b + 1 is converted while the tensor pipe works on block b ...
       if (b + 1 < nblocks) convert(b + 1);
-      GT_MARK(3, 100 * b + 3);
       // ... then block b's level-1 run (4 accumulations) is folded into the level-2 accumulator, round to nearest
       GT_WAIT(&bar_accfull, (uint32_t)b & 1u);
       tc_fence_after();
@@ -269,9 +254,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_accfree);
-      GT_MARK(3, 100 * b + 4);
     }
-    GT_MARK(3, 99998);
     // ---- flush the tile: float64 atomics, unscaled ----
     // (tcgen05.ld is warp-collective: every lane takes part, only the atomics are per valid atom)
     if (nblocks > 0) {
@@ -301,11 +284,9 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
       }
     }
   }
-  GT_MARK(warp == 16 ? 4 : 5, 1);
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tbase, 512);
-  GT_MARK(warp == 16 ? 6 : 7, 1);
 }
 
 // scales[0..3] from the maximum magnitudes of Z and X (powers of two: max |z'|, max |x'| in [256, 512))
@@ -370,31 +351,9 @@ int gram_tc_run(const float* z, const float* x, int64_t n, int d, int k, double*
   p.scales = scales;
   p.gzz = gzz;
   p.gzx = gzx;
-  p.dbg = nullptr;
-  static int* dbg_host = nullptr;
   const unsigned grid = (unsigned)(slabs * p.ntypes);
-  if (getenv("LASSO_B200_GRAM_DEBUG")) {
-    if (!dbg_host) LASSO_CUDA_TRY(cudaHostAlloc((void**)&dbg_host, 8 * 4 * 1024, cudaHostAllocMapped));
-    memset(dbg_host, 0, 8 * 4 * 1024);
-    int* ddev = nullptr;
-    LASSO_CUDA_TRY(cudaHostGetDevicePointer((void**)&ddev, dbg_host, 0));
-    p.dbg = ddev;
-  }
   LASSO_CUDA_TRY(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmem));
   gram_tc_kernel<<<grid, kGtThreads, kGtSmem, st>>>(p);
-  if (p.dbg) {
-    for (int i = 0; i < 300 && cudaStreamQuery(st) == cudaErrorNotReady; ++i) usleep(10000);
-    if (cudaStreamQuery(st) == cudaErrorNotReady) {
-      fprintf(stderr, "gram_tc_kernel still running after 3 s; grid %u ntypes %d slab_rows %lld\n", grid, p.ntypes, (long long)p.slab_rows);
-      for (unsigned c = 0; c < grid; ++c) {
-        const int* m = dbg_host + c * 8;
-        if (m[6] && m[7]) continue;
-        fprintf(stderr, "  cta %u: nblocks+1 %d alloc %d mma %d compute %d end(m,c) %d %d exit %d %d\n", c, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
-      }
-      fflush(stderr);
-      _exit(3);
-    }
-  }
   LASSO_CHECK_LAUNCH();
   count_launch(3);
   return LASSO_B200_OK;
