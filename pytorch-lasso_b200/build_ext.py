@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("LASSO_B200_LIB") or os.path.join(CSRC, "liblasso_b200.so")
-SOURCES = ["cabi.cu", "fista_ffma.cu", "fista_tc.cu", "fista_res.cu", "fista_blk.cu", "aux_kernels.cu", "conv_lip.cu", "ridge.cu", "gram_tc.cu", "fista_gram.cu"]
+SOURCES = ["cabi.cu", "fista_ffma.cu", "fista_tc.cu", "fista_res.cu", "fista_blk.cu", "aux_kernels.cu", "conv_lip.cu", "ridge.cu", "gram_tc.cu", "fista_gram.cu", "sweep_blk.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "lasso_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

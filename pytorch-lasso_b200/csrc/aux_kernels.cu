@@ -747,6 +747,13 @@ int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gz
 
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
                     const float* redraw, int* zeroed, int positive, cudaStream_t st) {
+  // default: the blocked sweep (sweep_blk.cu); LASSO_B200_SWEEP=legacy keeps the atom-by-atom kernels below
+  // (the tests compare the two)
+  {
+    const char* mode = getenv("LASSO_B200_SWEEP");
+    if (dict_update_blocked_supported(d, k) && !(mode && mode[0] == 'l'))
+      return dict_update_blocked_run(dict, gzz, gzx, d, k, eps, redraw, zeroed, positive, st);
+  }
   const size_t smem = sizeof(double) * ((size_t)kSweepDepth * (k + d) + d) +
                       sizeof(float) * ((size_t)d * k + k) + (size_t)k;
   if (smem <= 200 * 1024 && k <= 32 * kSweepMaxPerLane && (k % 2) == 0 && (d % 2) == 0 && k / 2 + d / 2 <= 1024) {

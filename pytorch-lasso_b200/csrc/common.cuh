@@ -163,6 +163,9 @@ int gram_tc_run(const float* z, const float* x, int64_t n, int d, int k, double*
 int gram_run(const float* z, const float* x, int64_t n, int d, int k, double* gzz,
              double* gzx, cudaStream_t st);
 int zero_columns_run(float* z, int64_t n, int k, const int* mask, cudaStream_t st);
+bool dict_update_blocked_supported(int d, int k);
+int dict_update_blocked_run(float* dict, double* gzz, double* gzx, int d, int k, double eps, const float* redraw,
+                            int* zeroed, int positive, cudaStream_t st);
 int dict_update_run(float* dict, double* gzz, double* gzx, int d, int k, double eps,
                     const float* redraw, int* zeroed, int positive, cudaStream_t st);
 

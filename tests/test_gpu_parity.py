@@ -522,6 +522,39 @@ def test_update_dict_large_dictionary_degenerate(dev):
         assert abs(float(got[:, j].norm()) - 1.0) <= 1e-6
 
 
+@pytest.mark.parametrize("n,d,k,positive", [(4096, 64, 256, False), (2000, 289, 300, False), (1500, 150, 300, True),
+                                           (600, 7, 19, False), (3000, 700, 96, False)])
+def test_blocked_sweep_equals_atom_by_atom_sweep(dev, monkeypatch, n, d, k, positive):
+    """sweep_blk.cu (blocks of atoms: one product for the block, then a serial chain of norms) against the
+    atom-by-atom kernels of aux_kernels.cu and the oracle's sequential update_dict, with unused atoms in the first,
+    a middle and the last block."""
+    x, w = make_problem(n, d, k, seed=21)
+    xd, wd = x.to(dev), w.to(dev)
+    z = sparse_encode(xd, wd, alpha=0.1, maxiter=20, tol=0.0)
+    unused = sorted({1, k // 2, k - 1})
+    z[:, unused] = 0
+    gzz, gzx = _cabi.gram(z, xd)
+    redraw = torch.randn(d, k, generator=torch.Generator().manual_seed(3)).to(dev)
+    out = {}
+    for mode in ("blocked", "legacy"):
+        if mode == "legacy":
+            monkeypatch.setenv("LASSO_B200_SWEEP", "legacy")
+        wm, a, b = wd.clone(), gzz.clone(), gzx.clone()
+        flags = _cabi.dict_update_gram(wm, a, b, redraw=redraw, positive=positive)
+        out[mode] = (wm, flags, a, b)
+    monkeypatch.delenv("LASSO_B200_SWEEP")
+    assert torch.equal(out["blocked"][1], out["legacy"][1])
+    assert sorted(torch.nonzero(out["blocked"][1]).flatten().tolist()) == unused
+    assert rel_fro(out["blocked"][0], out["legacy"][0]) <= 2e-6
+    assert torch.equal(out["blocked"][2], out["legacy"][2]) and torch.equal(out["blocked"][3], out["legacy"][3])
+    want = oracle.update_dict(w.clone(), x, z.cpu().clone(), positive=positive)
+    keep = [j for j in range(k) if j not in unused]
+    assert rel_fro(out["blocked"][0][:, keep], want[:, keep]) <= TOL
+    for j in unused:      # the replacement: the supplied draw, clamped if positive, unit norm
+        r = redraw[:, j].clamp_min(0) if positive else redraw[:, j]
+        assert rel_fro(out["blocked"][0][:, j], r / r.norm()) <= 1e-6
+
+
 def test_update_dict_positive(dev):
     # positive=True (dict_learning.py:87-88) against the reference's own output, on both sweep kernels
     g = load_golden("mstep_positive")
