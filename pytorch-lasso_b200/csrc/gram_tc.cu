@@ -3,8 +3,9 @@
 // contraction runs over the ROWS of the batch.
 //
 //   output tile   128 atoms (M) x 128 columns of [Z | X] (N); a CTA owns one tile for one slab of rows.
-//                 k <= 256, d <= 128: tiles (0,Z0) (0,Z1) (1,Z1) (0,X) (1,X); the off-diagonal Z tile is
-//                 mirrored into the lower triangle when it is flushed
+//                 k, d <= 512: the Z tiles on or above the diagonal and all X tiles (5 tile types at k = 256,
+//                 d = 64; 15 at the notebook's k = 300, d = 289); an off-diagonal Z tile is mirrored into the
+//                 lower triangle when it is flushed
 //   per 64 rows   A = Z^T block: thread = (atom, k-step of 16 rows) reads its 16 values (coalesced across
 //                 the atoms of a warp), splits them into fp16 pieces h + l and stores them to a TMEM stage
 //                 (the layout of the resident kernel's piece slots);
@@ -87,15 +88,27 @@ __device__ __forceinline__ void gsplit2(float2 v, uint32_t& wh, uint32_t& wl) {
   wl = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// tile type -> (atom offset of the M tile, kind of the N tile: 0 = Z columns at n0, 1 = X columns, mirror?)
-__device__ __forceinline__ void gram_tile(int type, int k, int& m0, int& n0, int& is_x, int& mirror) {
-  if (k <= 128) {            // (0,Z0) (0,X)
-    m0 = 0; n0 = 0; is_x = type == 1; mirror = 0;
-    return;
+// tile type -> (atom offset m0 of the M tile, column offset n0 of the N tile, N tile of Z or of X).
+// With MT = ceil(k / 128) M tiles: the Z tiles on or above the diagonal first, (0,0) (0,1) .. (0,MT-1) (1,1) ..,
+// then the MT x ceil(d / 128) X tiles.  k <= 256, d <= 128: (0,Z0) (0,Z1) (1,Z1) (0,X) (1,X).
+__host__ __device__ inline int gram_ntypes(int d, int k) {
+  const int mt = (k + 127) / 128, xt = (d + 127) / 128;
+  return mt * (mt + 1) / 2 + mt * xt;
+}
+__device__ __forceinline__ void gram_tile(int type, int d, int k, int& m0, int& n0, int& is_x) {
+  const int mt = (k + 127) / 128, xt = (d + 127) / 128;
+  const int nz = mt * (mt + 1) / 2;
+  if (type < nz) {
+    int row = 0, left = type;
+    while (left >= mt - row) {
+      left -= mt - row;
+      ++row;
+    }
+    m0 = row * 128; n0 = (row + left) * 128; is_x = 0;
+  } else {
+    const int e = type - nz;
+    m0 = (e / xt) * 128; n0 = (e % xt) * 128; is_x = 1;
   }
-  // (0,Z0) (0,Z1) (1,Z1) (0,X) (1,X)
-  const int mt[5] = {0, 0, 1, 0, 1}, nt[5] = {0, 1, 1, 0, 0}, xs[5] = {0, 0, 0, 1, 1};
-  m0 = mt[type] * 128; n0 = nt[type] * 128; is_x = xs[type]; mirror = type == 1;
 }
 
 __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) {
@@ -107,8 +120,8 @@ __global__ void __launch_bounds__(kGtThreads, 1) gram_tc_kernel(GramTcParams p) 
   const int64_t slab = blockIdx.x / p.ntypes;
   const int64_t r_begin = slab * p.slab_rows, r_end = min(p.n, r_begin + p.slab_rows);
   const int nblocks = r_begin < r_end ? (int)((r_end - r_begin + kGtRows - 1) / kGtRows) : 0;
-  int m0, n0, is_x, mirror;
-  gram_tile(type, p.k, m0, n0, is_x, mirror);
+  int m0, n0, is_x;
+  gram_tile(type, p.d, p.k, m0, n0, is_x);
 
   if (tid == 0) {
     mbar_init(&bar_full[0], 512);
@@ -322,7 +335,8 @@ __global__ void gram_scales_kernel(const unsigned* __restrict__ maxbits, float* 
 }  // namespace
 
 bool gram_tc_supported(int64_t n, int d, int k) {
-  return n >= 4096 && k >= 1 && k <= 256 && d >= 1 && d <= 128;
+  // (up to 4 x 4 tiles of 128: 26 tile types, still >= 5 slabs of rows on 148 SMs)
+  return n >= 4096 && k >= 1 && k <= 512 && d >= 1 && d <= 512;
 }
 
 // scratch: 64 bytes of device memory.  gzz / gzx must be zero on entry.
@@ -342,7 +356,7 @@ int gram_tc_run(const float* z, const float* x, int64_t n, int d, int k, double*
   p.n = n;
   p.d = d;
   p.k = k;
-  p.ntypes = k <= 128 ? 2 : 5;
+  p.ntypes = gram_ntypes(d, k);
   int64_t slabs = std::max<int64_t>(1, sms / p.ntypes);
   int64_t rows = (n + slabs - 1) / slabs;
   rows = ((rows + kGtRows - 1) / kGtRows) * kGtRows;

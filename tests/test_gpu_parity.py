@@ -943,10 +943,12 @@ def test_fused_ridge_start_not_positive_definite(dev):
 
 
 @pytest.mark.parametrize("n,d,k,density", [(131072, 64, 256, 0.08), (20000, 64, 256, 1.0), (9000, 24, 70, 0.1),
-                                           (5000, 128, 200, 0.3), (4100, 10, 128, 0.5)])
+                                           (5000, 128, 200, 0.3), (4100, 10, 128, 0.5),
+                                           (10000, 289, 300, 0.05),     # the notebook's shapes: 3 x 3 tiles of 128
+                                           (6000, 130, 512, 0.1), (4096, 512, 129, 0.2)])
 def test_tensor_core_gram_statistics(dev, monkeypatch, n, d, k, density):
     """K3 on tcgen05 (gram_tc.cu): Z^T Z and Z^T X against float64, and against the FFMA kernel it replaces for
-    k <= 256, d <= 128.  The round-toward-zero accumulate of the tensor core is confined to runs of 16
+    k <= 512, d <= 512.  The round-toward-zero accumulate of the tensor core is confined to runs of 16
     accumulations (two-level accumulation), which keeps the statistics within the 1e-6 they are tested to."""
     g = torch.Generator().manual_seed(n + k)
     z = torch.randn(n, k, generator=g) * (torch.rand(n, k, generator=g) < density) * 3.0
