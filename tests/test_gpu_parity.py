@@ -300,6 +300,10 @@ def test_gram_form_kernel_warm_start_stop_test_and_fallback(dev, monkeypatch):
     assert _cabi.resident_fallbacks() == before + 1
     ffma, _, _ = _cabi.fista_device(xd, wd, z0.to(dev), 0.1, lr, 9, True, -1.0, path="ffma")
     assert torch.equal(got, ffma)
+    # CPU tensors: the host entry point (H2D, solve on the Gram-form kernel, D2H), same codes as the device entry
+    z_host = ista(x, z0.clone(), w, alpha=0.1, lr=lr, maxiter=12, tol=0.0)
+    z_dev = ista(xd, z0.to(dev), wd, alpha=0.1, lr=lr, maxiter=12, tol=0.0)
+    assert not z_host.is_cuda and torch.equal(z_host, z_dev.cpu())
     # rows at wildly different scales: every row is rescaled on its own
     scale = 10.0 ** (8 * torch.rand(n, 1, generator=gen) - 4)
     got = ista(xd * scale.to(dev), torch.zeros(n, k, device=dev), wd, alpha=0.1, lr=lr, maxiter=30, tol=0.0)
