@@ -499,6 +499,7 @@ struct GfState {
   size_t b_cap = 0;
   float* beta = nullptr;
   int beta_cap = 0;
+  int beta_fast = -1;        // which table `beta` holds (-1: none); every table is a prefix of a longer one
   int num_sms = 0;
   long long* trace_host = nullptr;
   long long* trace_dev = nullptr;
@@ -584,9 +585,13 @@ int fista_gram_run(const FistaArgs& a, int* fell_back, cudaStream_t st) {
     const int cap = std::max(a.maxiter, 1024);
     LASSO_CUDA_TRY(cudaMalloc(&S.beta, sizeof(float) * (size_t)cap));
     S.beta_cap = cap;
+    S.beta_fast = -1;
   }
-  gf_beta_kernel<<<1, 1, 0, st>>>(S.beta, a.maxiter, a.fast);
-  LASSO_CHECK_LAUNCH();
+  if (S.beta_fast != (a.fast ? 1 : 0)) {      // once per device: a serial chain of float64 roots (0.27 us per entry)
+    gf_beta_kernel<<<1, 1, 0, st>>>(S.beta, S.beta_cap, a.fast ? 1 : 0);
+    LASSO_CHECK_LAUNCH();
+    S.beta_fast = a.fast ? 1 : 0;
+  }
   GfParams p{};
   p.image = S.image;
   p.b = S.b;

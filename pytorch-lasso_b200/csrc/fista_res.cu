@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
         }
         // ---------------- phase C (+ pieces of the next iteration) ----------------
         float part = 0.f, part_b = 0.f;   // two chains: 64 dependent adds per iteration otherwise
-        float2 moved2 = make_float2(0.f, 0.f);
+        bool moved_p = false;      // mode 2: a predicate register, not data registers (the kernel sits at its register cap)
 #pragma unroll
         for (int qi = 0; qi < 2; ++qi) {
           const int q = set + 2 * qi;
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
                   // mode 2 only asks whether anything moved: one packed multiply-add per pair on the FMA pipe
                   // (sum of squares; a non-zero dl is a difference of O(1) float32 numbers in scaled units,
                   // >= 1e-16, so its square cannot underflow) instead of OR-ing bit patterns on the ALU pipe
-                  if (kHist == 2) moved2 = __ffma2_rn(dl, dl, moved2);
+                  if (kHist == 2) moved_p = moved_p || (dl.x != 0.f) || (dl.y != 0.f);
                   const float2 yn = __ffma2_rn(beta2, dl, zn);           // ista.py:100
                   if (h2) { z4.z = zn.x; z4.w = zn.y; }
                   else { z4.x = zn.x; z4.y = zn.y; }
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
           } else {
-            s = __any_sync(0xffffffffu, moved2.x + moved2.y > 0.f) ? 1.f : 0.f;
+            s = __any_sync(0xffffffffu, moved_p) ? 1.f : 0.f;
           }
           if (lane == 0) {
             // the MMA warp adds the 16 partial records up after the next bar_rready; nobody comes after a
@@ -738,10 +738,22 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
 }
 
 // ---- set-up kernels ---------------------------------------------------------------------
-// scale of the dictionary (power of two, max |W'| in [8, 16)), scaled step / threshold, momentum
-// table, flag reset.  One block.
-__global__ void res_setup_kernel(const float* __restrict__ w, int nw, float lr, float lam, int iters, int fast,
-                                 ResScalars* __restrict__ sc, float* __restrict__ beta, int* __restrict__ flag) {
+// momentum table: python floats of ista.py:77-78, 98-101 (t0 = 1; beta_i = (t_i - 1) / t_{i+1}).  A serial chain of
+// float64 square roots and divisions (software sequences on this GPU: 55 us for 200 entries, 2 % of a config-2 solve
+// when it ran inside res_setup_kernel), but it depends on nothing but `fast` and every table is a prefix of a longer
+// one: computed once per device up to the buffer's capacity and kept.
+__global__ void res_beta_kernel(float* __restrict__ beta, int count, int fast) {
+  double t = 1.0;
+  for (int i = 0; i < count; ++i) {
+    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
+    beta[i] = fast ? (float)((t - 1.0) / t_next) : 0.f;
+    t = t_next;
+  }
+}
+
+// scale of the dictionary (power of two, max |W'| in [8, 16)), scaled step / threshold, flag reset.  One block.
+__global__ void res_setup_kernel(const float* __restrict__ w, int nw, float lr, float lam,
+                                 ResScalars* __restrict__ sc, int* __restrict__ flag) {
   __shared__ unsigned s_max;
   if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
@@ -763,13 +775,6 @@ __global__ void res_setup_kernel(const float* __restrict__ w, int nw, float lr, 
   if (!(sc->lr > 0.f) || !(sc->lr < 3.0e38f) || !(sc->lam < 3.0e38f) || (lam > 0.f && !(sc->lam > 0.f))) bad = 1;
   sc->bad = bad;
   *flag = bad;
-  // momentum: python floats of ista.py:77-78, 98-101 (t0 = 1; beta_i = (t_i - 1) / t_{i+1})
-  double t = 1.0;
-  for (int i = 0; i < iters; ++i) {
-    const double t_next = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
-    beta[i] = fast ? (float)((t - 1.0) / t_next) : 0.f;
-    t = t_next;
-  }
 }
 
 // dictionary [d][k] fp32 -> two scaled fp16 piece images, each [k/64 slabs][64 rows][128 B] with
@@ -810,6 +815,7 @@ struct ResState {
   int* flag = nullptr;
   float* beta = nullptr;
   int beta_cap = 0;
+  int beta_fast = -1;       // which table S.beta holds (-1: none)
   int num_sms = 0;
   bool attr_set = false;
   int* dbg_host = nullptr;
@@ -845,6 +851,13 @@ int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int ite
     const int cap = iters < 1024 ? 1024 : iters;
     LASSO_CUDA_TRY(cudaMalloc(&S.beta, sizeof(float) * (size_t)cap));
     S.beta_cap = cap;
+    S.beta_fast = -1;
+  }
+  if (S.beta_fast != (fast ? 1 : 0)) {        // (calls on one device are serialised and stream-ordered by the lease)
+    res_beta_kernel<<<1, 1, 0, st>>>(S.beta, S.beta_cap, fast ? 1 : 0);
+    LASSO_CHECK_LAUNCH();
+    count_launch();
+    S.beta_fast = fast ? 1 : 0;
   }
   if (!S.dbg_host && getenv("LASSO_B200_DEBUG")) {
     LASSO_CUDA_TRY(cudaHostAlloc((void**)&S.dbg_host, 4096, cudaHostAllocMapped));
@@ -864,7 +877,7 @@ int fista_res_prepare(const float* w, int d, int k, float lr, float lam, int ite
       LASSO_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesR));
     S.attr_set = true;
   }
-  res_setup_kernel<<<1, 256, 0, st>>>(w, d * k, lr, lam, iters, fast, S.scal, S.beta, S.flag);
+  res_setup_kernel<<<1, 256, 0, st>>>(w, d * k, lr, lam, S.scal, S.flag);
   LASSO_CHECK_LAUNCH();
   res_prep_w_kernel<<<(kDP * kKP + 255) / 256, 256, 0, st>>>(w, d, k, S.scal, S.w_image);
   LASSO_CHECK_LAUNCH();
