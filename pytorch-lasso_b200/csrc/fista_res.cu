@@ -716,10 +716,14 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
           } else {
             s = __any_sync(0xffffffffu, moved_p) ? 1.f : 0.f;
           }
-          if (lane == 0) {
+          // (lane and warp index are re-read here: kept across the iteration they cost two of the 96 registers and
+          // the record variants spilled loop-carried values into the iteration's critical path)
+          unsigned tid_now;
+          asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_now));
+          if ((tid_now & 31u) == 0u) {
             // the MMA warp adds the 16 partial records up after the next bar_rready; nobody comes after a
             // tile's last iteration, so there the warps add to the CTA's slot themselves
-            if (more) hist_s[it & 1][warp] = s;
+            if (more) hist_s[it & 1][tid_now >> 5] = s;
             else if (s != 0.f) atomicAdd(&p.part[(size_t)it * gridDim.x + blockIdx.x], (double)s);
           }
         }
