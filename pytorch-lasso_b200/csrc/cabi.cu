@@ -624,7 +624,17 @@ int host_pipeline(Workspace* ws, const float* x, const float* z0, float* z_out, 
     LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
     LASSO_CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
   }
-  const int64_t wave = fista_res_wave_rows(n), trows = fista_res_tile_rows(n);
+  // Waves of full-height tiles, the remainder in the LAST wave: a wave's duration does not depend on its tile height
+  // (a tile-iteration is a serial chain, not tensor-pipe bound), so the balanced split only made the last download --
+  // the part of the pipeline nothing overlaps -- as large as all the others.  LASSO_B200_PIPE=even: the balanced split.
+  int64_t wave = fista_res_wave_rows(n), trows = fista_res_tile_rows(n);
+  {
+    const char* pm = getenv("LASSO_B200_PIPE");
+    if (!(pm && pm[0] == 'e')) {
+      wave = (wave / trows) * 128;       // one 128-row tile per SM
+      trows = 0;                         // every launch picks its tile height from its own rows
+    }
+  }
   const int64_t nchunks = (n + wave - 1) / wave;
   const int slots = (int)std::min<int64_t>(kPipeSlots, nchunks);
   if ((rc = ensure(ws->hx, sizeof(float) * (size_t)slots * wave * d))) return rc;
