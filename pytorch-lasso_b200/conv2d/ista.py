@@ -22,13 +22,14 @@ import torch
 
 from .. import _cabi
 from ..linear import utils as _utils
-from .lip_const import lip_bound_conv2d, lip_constant
+from .lip_const import _one_int, lip_bound_conv2d, lip_constant
 
 __all__ = ["ista_conv2d"]
 
 
 def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
                 maxiter=10, lr='auto', tol=1e-5, verbose=False):
+    stride, padding = _one_int(stride), _one_int(padding)      # (s, s) / (p, p) as torch's conv2d takes them
     if lr == 'exact':
         # Extension (the reference has no such option): the exact constant lambda_max(conv2d^T conv2d) for
         # this image size, computed on the device -- any kernel size / stride / padding, e.g. BASELINE

@@ -14,6 +14,13 @@ from ..linear import utils as _utils
 __all__ = ["lip_bound_conv2d", "lip_constant"]
 
 
+def _one_int(value):
+    """torch's conv2d also takes a pair per axis; a pair of equal integers means the same thing as the integer."""
+    if isinstance(value, (tuple, list)) and len(value) == 2 and value[0] == value[1] and isinstance(value[0], int):
+        return value[0]
+    return value
+
+
 @torch.no_grad()
 def lip_constant(kernel, imsize, transpose=False, sqrt=False, stride=1, padding=0):
     """Largest eigenvalue of conv2d^T conv2d (``transpose=False``) / conv2d conv2d^T (``True``) on images
@@ -23,6 +30,7 @@ def lip_constant(kernel, imsize, transpose=False, sqrt=False, stride=1, padding=
     of the dictionary's Lipschitz constant).  Any kernel size, stride and padding (``stride`` / ``padding``
     are the reference's ``**kwargs``); ``cin*h*w <= 4096``.  Both operators share their non-zero spectrum, so
     ``transpose`` only says which side ``imsize`` describes: the image (False) or the code grid (True)."""
+    stride, padding = _one_int(stride), _one_int(padding)
     if not (isinstance(stride, int) and isinstance(padding, int)):
         raise NotImplementedError("one integer stride / padding for both axes")
     out_channels, in_channels, kh, kw = kernel.shape

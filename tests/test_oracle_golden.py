@@ -196,3 +196,8 @@ def test_conv2d_lip_bound_error_behaviour():
         ista_conv2d(torch.randn(1, 1, 9, 9), torch.zeros(1, 4, 7, 7), torch.randn(4, 1, 3, 3), stride=2, lr=0.1)
     z0 = torch.zeros(1, 4, 4, 4)
     assert ista_conv2d(torch.randn(1, 1, 9, 9), z0, torch.randn(4, 1, 3, 3), stride=2, lr=0.1, maxiter=0) is z0
+    # a pair of equal integers is the integer (torch's conv2d convention); unequal pairs are not built
+    assert ista_conv2d(torch.randn(1, 1, 9, 9), z0, torch.randn(4, 1, 3, 3), stride=(2, 2), padding=(0, 0), lr=0.1,
+                       maxiter=0) is z0
+    with pytest.raises(NotImplementedError):
+        ista_conv2d(torch.randn(1, 1, 9, 9), z0, torch.randn(4, 1, 3, 3), stride=(2, 1), lr=0.1)
