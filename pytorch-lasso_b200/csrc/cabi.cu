@@ -920,6 +920,10 @@ int32_t lasso_b200_gram_f32(const float* z, const float* x, int64_t n, int32_t d
     set_error("invalid argument to gram");
     return LASSO_B200_ERR_INVALID;
   }
+  // (the tensor-core kernel keeps its scales in per-device scratch: serialised like every other user of the workspace)
+  Lease ws;
+  int rc = ws.acquire((cudaStream_t)stream);
+  if (rc) return rc;
   return gram_run(z, x, n, d, k, gram_zz, gram_zx, (cudaStream_t)stream);
 }
 
@@ -931,6 +935,10 @@ int32_t lasso_b200_dict_update_gram_f32(float* dict, double* gram_zz, double* gr
     set_error("invalid argument to dict_update_gram");
     return LASSO_B200_ERR_INVALID;
   }
+  // (the blocked sweep keeps U0 and the dead-atom flags in per-device scratch)
+  Lease ws;
+  int rc = ws.acquire((cudaStream_t)stream);
+  if (rc) return rc;
   return dict_update_run(dict, gram_zz, gram_zx, d, k, eps, redraw, zeroed, positive ? 1 : 0, (cudaStream_t)stream);
 }
 
