@@ -17,9 +17,14 @@
 //             resident kernel); sg puts max |G'| in [256, 512); all powers of two, so every rescaling is exact.
 //             An iterate beyond the fp16 operand range raises a flag and the batch is solved again by the FFMA
 //             kernel (cabi.cu).
-// One launch per iteration (the stop test is batch-global); codes stay in caller units in HBM, so there is no
-// setup or unscale pass over them.  Per iteration a tile reads z_i, z_{i-1}, b and writes z_{i+1}: 4 x n k floats
-// (5 with the stop test, which re-reads z_i) plus the 2 x 2 x kpad x k bytes of G' per tile from L2.
+//   threads   8 compute warps with 168 registers each (lane = row of the tile; warps 0-3 / 4-7 take the even / odd
+//             32-atom units) + one issuer warp (slab copies, MMAs)
+// ALL iterations of a tile run in one launch: tiles are independent, and every thread reads back exactly the
+// elements it stored one iteration earlier.  The batch-global stop test is taken afterwards from the recorded sums
+// (the record of iteration i is summed while iteration i + 1 loads z_i and z_{i+1}); cabi.cu replays an early stop
+// with that iteration count.  Codes stay in caller units in HBM, so there is no set-up or unscale pass over them.
+// Per iteration a tile reads z_i, z_{i-1}, b and writes z_{i+1}: 4 x n k floats, plus the 2 x 2 x kpad x k bytes
+// of G' per tile from L2.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
