@@ -1,6 +1,6 @@
 // K4 (blocked): the Gauss-Seidel atom sweep of update_dict (dict_learning.py:82-101) in Gram space,
 //     u_j = B_j - sum_{l != j} d_l A_jl   (d_l already updated for l < j),   d_j <- u_j / |u_j|,
-// restructured so that the serial chain per atom is a norm and nothing else.
+// restructured so that the serial chain per atom is a short correction and a norm.
 //
 // The sweep kernels of aux_kernels.cu walk the atoms one by one and pay a d x k matrix-vector product plus
 // 3-4 CTA (or cluster) barriers per atom: 2.0 us per atom at d = 64, k = 256 and 2.7 us at d = 289, k = 300 --
@@ -11,8 +11,8 @@
 //           do; the subtraction from B_j in float64)
 //   phase B (one CTA, thread = row of the dictionary): atom by atom
 //           u_j = U0_j - sum_{l in block, l < j} (d_l^{new} - d_l^{start}) A_jl
-//           with the differences of the block's earlier atoms in REGISTERS (64 per thread), then the norm
-//           (one CTA barrier), the normalisation and the store.  A degenerate atom (|u| < eps,
+//           with the differences of the block's earlier atoms in a shared-memory column the thread owns, then the
+//           norm (float32 partial sums, one CTA barrier), the normalisation and the store.  A degenerate atom (|u| < eps,
 //           dict_learning.py:91-98) drops out of the statistics: its difference is -d_l^{start}, later blocks see
 //           its column of A as zero through the `dead` flags, and its row / column of the statistics are zeroed
 //           like the other kernels do; the replacement comes from `redraw` when the host supplies one.
