@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kMaxThreads) sweep_block_seq_kernel(float* __r
         const float4 a1 = *reinterpret_cast<const float4*>(&ajj[jj][l0 + 4]);
         float dv[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dv[e] = l0 + e < jj ? delta_s[(l0 + e) * dp + col] : 0.f;
+        for (int e = 0; e < 8; ++e) dv[e] = (row && l0 + e < jj) ? delta_s[(l0 + e) * dp + col] : 0.f;   // (idle threads read nothing)
         c0 = fmaf(dv[0], a0.x, c0); c1 = fmaf(dv[1], a0.y, c1);
         c0 = fmaf(dv[2], a0.z, c0); c1 = fmaf(dv[3], a0.w, c1);
         c0 = fmaf(dv[4], a1.x, c0); c1 = fmaf(dv[5], a1.y, c1);
