@@ -37,6 +37,7 @@ struct RateArgs {
   int ldst_reps;
   int do_store;     // 1: tcgen05.st instead of ld
   int b_mn_major;
+  int m;            // MMA M (128, or 64: half the TMEM lanes)
 };
 
 // warp 0: MMA issuer; warps 1..16: TMEM readers / writers (lane quadrant = warp % 4)
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(544) rate_kernel(RateArgs p) {
   long long my_cycles = 0;
   if (warp == 0) {
     if (p.mma_reps > 0) {
-      const uint32_t idesc = make_idesc(kFmtBF16, 128, p.n, 0, p.b_mn_major);
+      const uint32_t idesc = make_idesc(kFmtBF16, p.m, p.n, 0, p.b_mn_major);
       const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 16384;
       const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
       const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 0, 1024);
@@ -120,11 +121,11 @@ __global__ void __launch_bounds__(544) rate_kernel(RateArgs p) {
 }
 
 static void rate(const char* name, int n, int a_tmem, int mma_reps, int warps, int ldst_reps, int store,
-                 int b_mn, int grid = 1) {
+                 int b_mn, int grid = 1, int m = 128) {
   long long* d_out;
   CK(cudaMalloc(&d_out, 64));
   CK(cudaMemset(d_out, 0, 64));
-  RateArgs p{d_out, n, a_tmem, mma_reps, warps, ldst_reps, store, b_mn};
+  RateArgs p{d_out, n, a_tmem, mma_reps, warps, ldst_reps, store, b_mn, m};
   CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   rate_kernel<<<grid, 544, 65536>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
@@ -321,6 +322,10 @@ int main() {
     rate("T1 SS N=128", 128, 0, 512, 0, 0, 0, 0, grid);
     rate("T1 SS N=256", 256, 0, 512, 0, 0, 0, 0, grid);
   }
+  // M = 64: does a half-height MMA cost half?  (it would decide whether two interleaved 64-row tiles per CTA pay)
+  rate("T1 TS N=64 M=64", 64, 1, 512, 0, 0, 0, 1, 1, 64);
+  rate("T1 TS N=128 M=64", 128, 1, 512, 0, 0, 0, 1, 1, 64);
+  rate("T1 SS N=64 M=64", 64, 0, 512, 0, 0, 0, 1, 1, 64);
   for (int w : {1, 4, 8, 16}) rate("T2 tmem ld x32", 64, 1, 0, w, 256, 0, 0);
   for (int w : {1, 4, 8, 16}) rate("T2 tmem st x32", 64, 1, 0, w, 256, 1, 0);
   rate("T3 TS N=64 + 16 warps ld", 64, 1, 512, 16, 256, 0, 0);
