@@ -44,8 +44,6 @@ def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
         lr = 1 / float(lip_bound_conv2d(weight, padding))      # ista.py:13-15 (odd kernels only)
     if not (isinstance(stride, int) and isinstance(padding, int)) or stride < 1 or padding < 0:
         raise NotImplementedError("lasso_b200.conv2d takes one integer stride >= 1 and padding >= 0 for both axes")
-    if verbose:
-        raise NotImplementedError("verbose=True is not built for the convolutional path")
     for name, t in (("x", x), ("z0", z0), ("weight", weight)):
         if t.dtype != torch.float32:
             raise NotImplementedError("lasso_b200 computes in float32 only; {} has dtype {}".format(name, t.dtype))
@@ -69,7 +67,29 @@ def ista_conv2d(x, z0, weight, alpha=1.0, stride=1, padding=0, fast=True,
     z_rows = z0.to(dev).permute(0, 2, 3, 1).reshape(n * oh * ow, filters).contiguous()
     if not bool(z_rows.any()):
         z_rows = None                                          # zero start: the kernel clears its own buffer
-    out_rows, _ = _cabi.conv2d_fista_device(x.to(dev).contiguous(), w_lin, z_rows, kh, kw, alpha, float(lr),
-                                            maxiter, fast, tol_abs, stride=stride, padding=padding)
+    xd = x.to(dev).contiguous()
+    out_rows, done = _cabi.conv2d_fista_device(xd, w_lin, z_rows, kh, kw, alpha, float(lr), maxiter, fast, tol_abs,
+                                               want_iters=verbose, stride=stride, padding=padding)
     z = out_rows.reshape(n, oh, ow, filters).permute(0, 3, 1, 2).contiguous()
+    if verbose:
+        # 'loss: %0.4f' of the iterate each executed iteration starts from (ista.py:21-24, 36-38).  The kernel keeps
+        # all iterations on the device, so the i-th iterate is produced by a run of i iterations (deterministic
+        # kernels: the same iterate the long run passed through) -- a debugging aid, quadratic in maxiter.
+        import torch.nn.functional as F
+        wd = weight.to(dev)
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            for i in range(done):
+                if i == 0:
+                    zi = z0.to(dev)
+                else:
+                    rows, _ = _cabi.conv2d_fista_device(xd, w_lin, z_rows, kh, kw, alpha, float(lr), i, fast, -1.0,
+                                                        stride=stride, padding=padding)
+                    zi = rows.reshape(n, oh, ow, filters).permute(0, 3, 1, 2)
+                x_hat = F.conv_transpose2d(zi, wd, stride=stride, padding=padding)
+                loss = (0.5 * (xd - x_hat).pow(2).sum() + alpha * zi.abs().sum()) / n
+                print('loss: %0.4f' % float(loss))
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
     return z if x.is_cuda else z.cpu()

@@ -898,6 +898,28 @@ def test_conv2d_exact_lipschitz_constant(dev, filters, cin, ks, size, stride, pa
     assert abs(got_t ** 2 - want) <= 1e-4 * want
 
 
+@pytest.mark.parametrize("name", ["conv_4x4_stride2_pad1", "conv_8x8_fista", "conv_3x3_auto_earlystop"])
+def test_conv2d_verbose_prints_the_reference_losses(dev, capsys, name):
+    """verbose=True (lasso/conv2d/ista.py:21-24, 36-38): 'loss: %0.4f' of the iterate every executed iteration starts
+    from -- against the oracle's iterates, one line per executed iteration (the early-stop fixture stops the prints)."""
+    import torch.nn.functional as F
+    from lasso_b200.conv2d import ista_conv2d, lip_bound_conv2d
+    g = load_golden(name)
+    stride, padding = int(g.get("stride", 1)), int(g.get("padding", 0))
+    lr = g["lr"] if g["lr"] > 0 else 1 / float(lip_bound_conv2d(g["weight"], padding))
+    kw = dict(alpha=g["alpha"], stride=stride, padding=padding, fast=bool(g["fast"]), lr=lr, tol=g["tol"])
+    z = ista_conv2d(g["x"].to(dev), g["z0"].to(dev), g["weight"].to(dev), maxiter=int(g["maxiter"]), verbose=True, **kw)
+    printed = [l for l in capsys.readouterr().out.splitlines() if l.startswith("loss: ")]
+    assert rel_fro(z, g["z"]) <= TOL
+    _, done = oracle.conv2d_ista(g["x"], g["z0"], g["weight"], maxiter=int(g["maxiter"]), return_iters=True, **kw)
+    assert len(printed) == done
+    for i, line in enumerate(printed):
+        zi = g["z0"] if i == 0 else oracle.conv2d_ista(g["x"], g["z0"], g["weight"], maxiter=i, **dict(kw, tol=-1.0))
+        x_hat = F.conv_transpose2d(zi, g["weight"], stride=stride, padding=padding)
+        want = float((0.5 * (g["x"] - x_hat).pow(2).sum() + g["alpha"] * zi.abs().sum()) / g["x"].size(0))
+        assert abs(float(line.split()[1]) - want) <= 1e-4 + 2e-5 * abs(want), (i, line, want)
+
+
 def test_conv2d_lr_exact_for_even_kernels(dev):
     """lr='exact': config 5's 8x8 filters get an automatic step (lr='auto' raises for even kernels, like the
     reference: lip_const.py:101-102); the solve equals the oracle run with the same step."""
