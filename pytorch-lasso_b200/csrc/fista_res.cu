@@ -194,12 +194,22 @@ __device__ __forceinline__ void store4(float* __restrict__ rowp, int c, int cols
 }
 
 // Tile load / store live in their own (non-inlined) functions: they run once per tile and solve,
-// and kept inline they cost the iteration loop registers (6 % at C2).
+// and kept inline they cost the iteration loop registers (6 % at C2).  They take what they need BY VALUE: a
+// reference to the kernel's parameter struct forces the whole struct into local memory, and every p.field in the
+// iteration loop then becomes a local-memory load instead of a constant-bank operand.
+struct TileIo {
+  const float* x;
+  const float* z0;
+  float* z_out;
+  int d, k;
+  int vec_x, vec_z0, vec_z;
+  float limit;
+};
 //
 // Row r is scaled by sx_r = 2^(6 - exponent(max |x_r|)) (max |x'_r| in [64, 128)); its codes then
 // live in units of sx_r / sw.  A row's result depends on that row alone, so any row split of a
 // batch gives the same bits.
-__device__ __noinline__ void res_load_tile(const ResParams& p, uint8_t* xs, uint8_t* zs, float* row_sx,
+__device__ __noinline__ void res_load_tile(const TileIo p, uint8_t* xs, uint8_t* zs, float* row_sx,
                                            int64_t row0, int valid, float isw, int ct) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -236,7 +246,7 @@ __device__ __noinline__ void res_load_tile(const ResParams& p, uint8_t* xs, uint
 }
 
 // returns true when a code is inf / NaN / beyond the limit: an operand left the fp16 range
-__device__ __noinline__ bool res_store_tile(const ResParams& p, const uint8_t* zs, const float* row_sx,
+__device__ __noinline__ bool res_store_tile(const TileIo p, const uint8_t* zs, const float* row_sx,
                                             int64_t row0, int valid, float sw, int ct) {
   bool bad = false;
 #pragma unroll 4
@@ -508,7 +518,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       int valid = p.trows;
       if (row0 + valid > p.n) valid = (int)(p.n - row0);
       // ---------------- load the tile: x and z0, rescaled per row ----------------
-      res_load_tile(p, xs, zs, row_sx, row0, valid, sc.isw, ct);
+      res_load_tile(TileIo{p.x, p.z0, p.z_out, p.d, p.k, p.vec_x, p.vec_z0, p.vec_z, p.limit}, xs, zs, row_sx, row0, valid,
+                    sc.isw, ct);
       const float lam = sc.lam * row_sx[row];           // lam sx_r / sw
       const float uz_row = sc.sw / row_sx[row];         // code units -> caller units (exact)
       // ---------------- y_0 = z_0 (ista.py:76) and its pieces ----------------
@@ -731,7 +742,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) fista_res_kernel(ResParams p) {
       }
       // ---------------- store the codes ----------------
       compute_sync();
-      bad |= res_store_tile(p, zs, row_sx, row0, valid, sc.sw, ct);
+      bad |= res_store_tile(TileIo{p.x, p.z0, p.z_out, p.d, p.k, p.vec_x, p.vec_z0, p.vec_z, p.limit}, zs, row_sx, row0,
+                            valid, sc.sw, ct);
       compute_sync();
     }
     if (bad) atomicExch(p.flag, 1);
