@@ -43,14 +43,18 @@ peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_P
 path_name = {1: "ffma", 2: "tcgen05", 3: "resident", 4: "blocked"}[
     _cabi.select_path(n, d, k) if args.path == "auto" else _cabi.path_code(args.path)]
 step_us = ms * 1e3 / args.iters
-alg_bytes = n * (d + (5 if path_name == "blocked" else 3) * k) * 4
+alg_bytes = n * (d + 3 * k) * 4                                   # read x, z_i, z_{i-1}, write z_{i+1}
+moved_bytes = n * (d + (5 if path_name == "blocked" else 3) * k) * 4   # the blocked kernel reads both code buffers twice
 line = {"workload": "configs[2]: FISTA n=262144 d=128 k=1024 alpha=0.05 fp32 codes, %d iterations, tol disabled, lr pinned" % args.iters,
         "kernel_path": path_name, "value": args.iters / (ms * 1e-3), "unit": "iters/s", "us_per_iter": step_us,
         "gpu_launches": int(launches), "rel_err_vs_oracle_on_256_rows": err,
         "roofline": {"bound": "hbm", "achieved": alg_bytes / (step_us * 1e-6) / 1e9, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": alg_bytes / (step_us * 1e-6) / 1e9 / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "n (d + 5k) floats per iteration: both code buffers are read in both passes; "
+                     "moved_bytes_per_launch": moved_bytes,
+                     "frac_on_moved_bytes": moved_bytes / (step_us * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                     "note": "frac = algorithmic n (d + 3k) floats per iteration / time / measured copy bandwidth; the "
+                             "k-blocked kernel moves n (d + 5k): both code buffers are read in both passes; "
                              "the dictionary slices (1 MB per tile and iteration) come from L2"},
         "tensor": {"algorithmic_tflops": 4.0 * n * d * k * args.iters / (ms * 1e-3) / 1e12}}
 if not args.no_cpu:
