@@ -306,3 +306,71 @@ def test_sharded_dict_learning_one_all_reduce_per_step(tmp_path, tol):
     else:
         assert 1 + steps <= n_ar <= 1 + 2 * steps
     assert parts[0]["calls"]["broadcast"] == 1
+
+
+@pytest.mark.parametrize("block", [1, 7, 64])
+def test_blocked_gauss_seidel_is_the_sequential_sweep(block):
+    """The algebra behind csrc/sweep_blk.cu, restated in float64 on the CPU: taking the atoms in blocks -- the part
+    of u_j that does not depend on the block's own updates as ONE product for the whole block, then per atom only the
+    corrections (d_l_new - d_l_start) A_jl of the block's earlier atoms -- is the sequential Gauss-Seidel sweep of
+    update_dict in Gram space (oracle.update_dict_gram, dict_learning.py:82-101), unused atoms included: a degenerate
+    atom's difference is -d_l_start, later blocks see its column of A as zero."""
+    g = torch.Generator().manual_seed(4)
+    n, d, k = 400, 9, 23
+    z = torch.randn(n, k, generator=g, dtype=torch.float64) * (torch.rand(n, k, generator=g) < 0.3)
+    unused = [0, 8, 22]
+    z[:, unused] = 0
+    x = torch.randn(n, d, generator=g, dtype=torch.float64)
+    w0 = torch.nn.functional.normalize(torch.randn(d, k, generator=g, dtype=torch.float64), dim=0)
+    a, b = z.T @ z, z.T @ x
+    draws = torch.randn(d, k, generator=g, dtype=torch.float64)
+    it = iter(unused)
+    want, zeroed = oracle.update_dict_gram(w0, a, b, redraw=lambda m: draws[:, next(it)])
+    assert zeroed == unused
+
+    dmat, dead = w0.clone(), torch.zeros(k, dtype=torch.bool)
+    for j0 in range(0, k, block):
+        blk = range(j0, min(j0 + block, k))
+        amask = a.clone()
+        amask[:, dead] = 0                      # later blocks see a dead atom's column as zero
+        u0 = {j: b[j] - dmat @ amask[j] + amask[j, j] * dmat[:, j] for j in blk}      # one product per block
+        start, delta = dmat.clone(), {}
+        for j in blk:
+            u = u0[j] - sum(delta[l] * a[j, l] for l in delta)
+            nrm = u.norm()
+            if nrm < 1e-10:
+                new = draws[:, j] / draws[:, j].norm()
+                dead[j] = True
+                delta[j] = -start[:, j]         # takes the atom's start value out of the later atoms' U0
+            else:
+                new = u / nrm
+                delta[j] = new - start[:, j]
+            dmat[:, j] = new
+    assert sorted(torch.nonzero(dead).flatten().tolist()) == unused
+    assert rel_fro(dmat, want) <= 1e-12
+
+
+@pytest.mark.parametrize("gap", [1e-2, 1e-4, 1.2e-7, 1e-9])
+def test_lipschitz_scheme_error_bound(gap):
+    """The scheme of K2 (csrc/aux_kernels.cu), restated on the CPU: float32 power iteration on the 4096th power of the
+    Gram (twelve trace-normalised squarings in float32), at most 256 steps, then ONE float64 Rayleigh quotient on the
+    original Gram.  For any relative gap g between the two largest eigenvalues the quotient is off by at most
+    g exp(-2 * 4096 * 256 g) <= 1.8e-7 -- including the gap that maximises that expression (1.2e-7)."""
+    g = torch.Generator().manual_seed(11)
+    m = 60
+    q, _ = torch.linalg.qr(torch.randn(m, m, generator=g, dtype=torch.float64))
+    ev = torch.linspace(1.0, 0.05, m, dtype=torch.float64)
+    ev[0], ev[1] = 1.0, 1.0 - gap
+    gram = (q * ev) @ q.T
+    gram = 0.5 * (gram + gram.T)
+    b = gram.to(torch.float32)
+    for _ in range(12):
+        b = b / b.diagonal().sum()
+        b = b @ b
+    v = torch.ones(m, dtype=torch.float32) + 0.25 * torch.rand(m, generator=g)
+    for _ in range(256):
+        u = b @ v
+        v = u / u.norm()
+    v64 = v.double()
+    lam = float(v64 @ gram @ v64 / (v64 @ v64))
+    assert 0.0 <= 1.0 - lam <= 2.5e-7
