@@ -374,3 +374,47 @@ def test_lipschitz_scheme_error_bound(gap):
     v64 = v.double()
     lam = float(v64 @ gram @ v64 / (v64 @ v64))
     assert 0.0 <= 1.0 - lam <= 2.5e-7
+
+
+def test_gram_form_restatement_and_deferred_stop_test():
+    """The algorithm of csrc/fista_gram.cu restated on the CPU in float64: the gradient y (W^T W) - x W is the
+    reference's (y W^T - x) W (ista.py:71-73); the stop-test record of iteration i is taken while iteration i + 1 forms
+    its extrapolation (|z_i - z_{i+1}| of the two buffers it reads anyway), one closing pass takes the last one; and
+    running all iterations, reading the records and replaying with the count they give returns what the reference's
+    in-place stop returns (ista.py:93-95)."""
+    n, d, k, alpha, maxiter, tol = 60, 40, 24, 0.2, 200, 1e-4
+    x, w = make_problem(n, d, k, seed=9, kind="planted")
+    lr = 1.0 / oracle.lipschitz_constant(w)
+    want, done, deltas = oracle.ista(x, torch.zeros(n, k), w, alpha=alpha, fast=True, lr=lr, maxiter=maxiter, tol=tol,
+                                     return_info=True)
+    assert 1 < done < maxiter
+    x64, w64 = x.double(), w.double()
+    gw, bxw = w64.T @ w64, x64 @ w64
+    lr32, lam = float(torch.tensor(lr, dtype=torch.float32)), float(torch.tensor(alpha * lr, dtype=torch.float32))
+
+    def run(iters):
+        bufs = [torch.zeros(n, k, dtype=torch.float64), torch.zeros(n, k, dtype=torch.float64)]
+        hist, t = [0.0] * iters, 1.0
+        for it in range(iters + 1):
+            zc, zp = bufs[it & 1], bufs[(it & 1) ^ 1]
+            if it > 0:
+                hist[it - 1] = float((zp - zc).abs().sum())       # the previous iteration's record
+            if it == iters:
+                break
+            beta = 0.0
+            if it > 0:
+                t_next = (1 + math.sqrt(1 + 4 * t * t)) / 2
+                beta, t = (t - 1) / t_next, t_next
+            y = zc + beta * (zc - zp)
+            grad = y @ gw - bxw
+            assert rel_fro(grad, (y @ w64.T - x64) @ w64) <= 1e-12
+            bufs[(it & 1) ^ 1] = torch.nn.functional.softshrink(y - lr32 * grad, lam)
+        return bufs[iters & 1], hist
+
+    _, hist = run(maxiter)
+    stop = next(i + 1 for i, h in enumerate(hist) if h <= n * k * tol)
+    assert stop == done
+    z, hist2 = run(stop)
+    assert rel_fro(z.float(), want) <= 2e-6
+    assert torch.allclose(torch.tensor(hist2[:stop - 1], dtype=torch.float64),
+                          torch.tensor([float(v) for v in deltas[:stop - 1]], dtype=torch.float64), rtol=1e-3)
